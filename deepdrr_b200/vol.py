@@ -1,0 +1,141 @@
+"""Volume data contract at the projector boundary (host side, NumPy).
+
+Only what the projection path consumes from the reference's ``deepdrr.vol`` package:
+
+* ``Volume.data``       float32 ``[Ni, Nj, Nk]`` densities (g/cm^3)          (vol/volume.py:178-179)
+* ``Volume.materials``  ``(dict name -> id, uint16 labels [Ni, Nj, Nk])``    (vol/volume.py:181-184)
+* pose: ``world_from_IJK = world_from_anatomical @ anatomical_from_IJK``      (vol/renderable.py:58-84)
+* ``enabled`` flag                                                           (vol/volume.py:190-192)
+
+plus the two conversions the synthetic configs need: HU -> density (vol/volume.py:338-351) and
+threshold segmentation (load_dicom.py:132-143).  Loaders (NIfTI/NRRD/DICOM), mesh tooling and the
+V-Net segmentation are out of scope.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+
+from . import geo
+
+
+class Renderable:
+    """Pose bookkeeping shared by volumes and meshes (reference: vol/renderable.py:33-84)."""
+
+    def __init__(self, anatomical_from_IJK=None, world_from_anatomical=None, anatomical_from_ijk=None,
+                 enabled: bool = True):
+        if anatomical_from_ijk is not None:
+            anatomical_from_IJK = anatomical_from_ijk
+        self.anatomical_from_IJK = geo.frame_transform(anatomical_from_IJK)
+        self.world_from_anatomical = geo.frame_transform(world_from_anatomical)
+        self.enabled = enabled
+
+    def set_enabled(self, enabled: bool) -> None:
+        self.enabled = enabled
+
+    @property
+    def anatomical_from_ijk(self):
+        return self.anatomical_from_IJK
+
+    @property
+    def world_from_IJK(self) -> geo.FrameTransform:
+        return self.world_from_anatomical @ self.anatomical_from_IJK
+
+    @property
+    def world_from_ijk(self) -> geo.FrameTransform:
+        return self.world_from_IJK
+
+    @property
+    def IJK_from_world(self) -> geo.FrameTransform:
+        return self.world_from_IJK.inverse()
+
+    @property
+    def ijk_from_world(self) -> geo.FrameTransform:
+        return self.world_from_IJK.inv
+
+    # pose helpers used by user scripts (subset of vol/renderable.py:150-234)
+    def place_center(self, x) -> None:
+        x = np.asarray(x, dtype=np.float64).reshape(-1)[:3]
+        center_anat = self.anatomical_from_IJK @ (np.array(self.shape, dtype=np.float64) / 2)
+        center_world = self.world_from_anatomical @ center_anat
+        self.translate(x - center_world)
+
+    def translate(self, t) -> None:
+        t = np.asarray(t, dtype=np.float64).reshape(-1)[:3]
+        self.world_from_anatomical = geo.FrameTransform.from_translation(t) @ self.world_from_anatomical
+
+    def rotate(self, rotation, center=None) -> None:
+        r = rotation.as_matrix() if hasattr(rotation, "as_matrix") else np.asarray(rotation, dtype=np.float64)
+        c = np.zeros(3) if center is None else np.asarray(center, dtype=np.float64).reshape(-1)[:3]
+        m = geo.FrameTransform.from_translation(c) @ geo.FrameTransform.from_rt(r) @ geo.FrameTransform.from_translation(-c)
+        self.world_from_anatomical = m @ self.world_from_anatomical
+
+
+def convert_hounsfield_to_density(hu_values: np.ndarray, smooth_air: bool = False) -> np.ndarray:
+    """Two-segment linear HU -> g/cm^3 map, clamped at 0 (reference: vol/volume.py:338-351)."""
+    if smooth_air:
+        hu_values[hu_values <= -900] = -1000
+    return np.maximum(np.minimum(0.001029 * hu_values + 1.030, 0.0005886 * hu_values + 1.03), 0)
+
+
+def segment_materials_thresholding(hu_values: np.ndarray) -> Dict[str, np.ndarray]:
+    """air <= -800 < soft tissue <= 350 < bone (reference: load_dicom.py:132-143)."""
+    materials = {}
+    materials["air"] = hu_values <= -800
+    materials["soft tissue"] = (-800 < hu_values) * (hu_values <= 350)
+    materials["bone"] = 350 < hu_values
+    return materials
+
+
+def format_materials(materials: Dict[str, np.ndarray]) -> Tuple[Dict[str, int], np.ndarray]:
+    """dict of masks -> (name -> id, uint16 labels); later masks overwrite earlier ones and
+    unlabeled voxels stay 0 (reference: vol/volume.py:955-992)."""
+    combined = None
+    mdict: Dict[str, int] = {}
+    for mat_id, mat in enumerate(materials):
+        if combined is None:
+            combined = np.zeros(materials[mat].shape, dtype=np.uint16)
+        combined[materials[mat] > 0] = mat_id
+        mdict[mat] = mat_id
+    return mdict, combined
+
+
+class Volume(Renderable):
+    """Density volume + material labels + pose (reference: vol/volume.py:142-192)."""
+
+    def __init__(self, data: np.ndarray,
+                 materials: Union[Dict[str, np.ndarray], Tuple[Dict[str, int], np.ndarray]],
+                 anatomical_from_IJK=None, world_from_anatomical=None,
+                 anatomical_coordinate_system: Optional[str] = None, enabled: bool = True, **kwargs):
+        Renderable.__init__(self, anatomical_from_IJK, world_from_anatomical, enabled=enabled, **kwargs)
+        assert np.ndim(data) == 3, "Volume data must be 3D."
+        self.data = np.array(data).astype(np.float32)
+        if isinstance(materials, tuple):
+            self.materials = materials[0], np.asarray(materials[1]).astype(np.uint16)
+        else:
+            self.materials = format_materials(materials)
+        assert anatomical_coordinate_system in ["LPS", "RAS", None]
+        self.anatomical_coordinate_system = anatomical_coordinate_system
+
+    @classmethod
+    def from_hu(cls, hu_values: np.ndarray, anatomical_from_IJK=None, world_from_anatomical=None, **kwargs):
+        """HU volume -> Volume with threshold segmentation (reference: vol/volume.py:194-260 with
+        ``use_thresholding=True``)."""
+        data = convert_hounsfield_to_density(hu_values)
+        materials = segment_materials_thresholding(hu_values)
+        return cls(data, materials, anatomical_from_IJK, world_from_anatomical, **kwargs)
+
+    @property
+    def shape(self) -> Tuple[int, int, int]:
+        return self.data.shape
+
+    @property
+    def spacing(self) -> np.ndarray:
+        return np.abs(np.array(self.anatomical_from_IJK.R)).max(axis=0)
+
+    def __array__(self, dtype=None, copy=None) -> np.ndarray:
+        return self.data if dtype is None else self.data.astype(dtype)
+
+    def get_center(self) -> np.ndarray:
+        return self.anatomical_from_IJK @ (np.array(self.shape, dtype=np.float64) / 2)
