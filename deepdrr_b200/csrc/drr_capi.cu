@@ -1,0 +1,530 @@
+// C ABI of libdrr_b200.so (include/drr_b200.h): handle management, volume upload / cell-record
+// construction, batch projection.  Host side of the B200-native replacement for the GPU glue in
+// /root/reference/deepdrr/projector/projector.py (initialize 1395-1717, project 655-800, free 1719-1764).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "drr_device.cuh"
+
+// kernels / launchers defined in the other translation units
+cudaError_t drr_launch_march_single(const MarchParams& P, int grid, cudaStream_t s);
+cudaError_t drr_launch_march_general(const MarchParams& P, cudaStream_t s);
+int drr_march_single_occupancy(int M);
+cudaError_t drr_launch_spectral(const float* area, int n_bins, int M, const float* energies, const float* pdf, const float* mu,
+                                size_t npix, int n_views, float* intensity, float* pprob, int n_sm, cudaStream_t s);
+cudaError_t drr_launch_noise(float* intensity, const float* pprob, float* scratch, int W, int H, int n_views, float photon_count,
+                             unsigned long long seed, cudaStream_t s);
+cudaError_t drr_launch_clip(float* img, size_t total, float upper, cudaStream_t s);
+cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* minmax, float epsilon, cudaStream_t s);
+cudaError_t drr_launch_collected(float* intensity, float* solid, double* view_sum, const ViewDev* views, int W, int H, int n_views,
+                                 float photon_count, float pixel_area, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// upload kernels
+// ---------------------------------------------------------------------------------------------
+// [ni][nj][nk] (k fastest, NumPy order of Volume.data) -> [nk][nj][ni] (i fastest, texture order;
+// the reference does this with cupy.moveaxis, projector.py:1468-1470 / 1509).
+template <typename T>
+__global__ void transpose_ik_kernel(const T* __restrict__ in, T* __restrict__ out, int ni, int nj, int nk) {
+    __shared__ T tile[32][33];
+    const int j = blockIdx.z;
+    const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r, k = k0 + threadIdx.x;
+        if (i < ni && k < nk) tile[r][threadIdx.x] = in[((size_t)i * nj + j) * nk + k];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, i = i0 + threadIdx.x;
+        if (i < ni && k < nk) out[((size_t)k * nj + j) * ni + i] = tile[threadIdx.x][r];
+    }
+}
+
+// One thread per cell base (bi, bj, bk) in [-2, n-2]^3: gathers the 8 clamped corner texels / labels
+// and stores the filter-coefficient record (see hw_trilinear_cell) and the label record.
+__global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t* __restrict__ lab, int ni, int nj, int nk,
+                                   float4* __restrict__ cellc, uint2* __restrict__ celll) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cj = blockIdx.y, ck = blockIdx.z;
+    if (ci > ni) return;
+    const int bi = ci - 2, bj = cj - 2, bk = ck - 2;
+    float T[2][2][2];  // [z][x][y]
+    unsigned lx = 0, ly = 0;
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                int i = max(0, min(bi + a, ni - 1)), j = max(0, min(bj + b, nj - 1)), k = max(0, min(bk + c, nk - 1));
+                size_t o = ((size_t)k * nj + j) * ni + i;
+                T[c][a][b] = dens[o];
+                unsigned l = lab[o];
+                if (c) ly |= l << (8 * (a + 2 * b)); else lx |= l << (8 * (a + 2 * b));
+            }
+    const size_t cell = ((size_t)ck * (nj + 1) + cj) * (ni + 1) + ci;
+    const float s = 1.0f / 256.0f;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        float t01 = T[c][0][1], t10 = T[c][1][0], t00 = T[c][0][0], t11 = T[c][1][1];
+        cellc[2 * cell + c] = make_float4(t01 * s, (t10 - t01) * s, (t00 - t01) * s, (t11 - t10) * s);
+    }
+    celll[cell] = make_uint2(lx, ly);
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct VolHost {
+    float* dens = nullptr;
+    uint8_t* lab = nullptr;
+    float4* cellc = nullptr;
+    uint2* celll = nullptr;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    int ni = 0, nj = 0, nk = 0;
+};
+
+struct drr_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    // spectrum
+    int n_bins = 0, M = 0;
+    float *d_energies = nullptr, *d_pdf = nullptr, *d_mu = nullptr;
+    // volumes
+    std::vector<VolHost> vols;
+    int priority[DRR_MAX_VOLUMES];
+    int enabled[DRR_MAX_VOLUMES];
+    bool priorities_set = false;
+    // march options
+    float step = 0.1f;
+    int attenuate_outside = 0, air_index = 0, sampler = DRR_SAMPLER_HYBRID;
+    int tex_eighths = 3;
+    // mesh buffers (device pointers, possibly owned)
+    int mesh_layers = 0, max_hits = 0, n_mesh_mats = 0;
+    const float* hit_alphas = nullptr;
+    const int8_t* hit_facing = nullptr;
+    const int8_t* layer_valid = nullptr;
+    const float* additive = nullptr;
+    const int* mesh_mats = nullptr;
+    std::vector<void*> mesh_owned;
+    // per-batch scratch (grown on demand)
+    ViewDev* d_views = nullptr; ViewDev* h_views = nullptr; int views_cap = 0;
+    float *d_area = nullptr, *d_intensity = nullptr, *d_pprob = nullptr, *d_scratch = nullptr;
+    size_t area_cap = 0, int_cap = 0, pp_cap = 0, scratch_cap = 0;
+    unsigned* d_minmax = nullptr; double* d_viewsum = nullptr; int minmax_cap = 0;
+    unsigned long long* d_samples = nullptr;
+    unsigned int* d_tile_counter = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[3] = {0, 0, 0};
+    unsigned long long last_samples = 0, launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(drr_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(c, x)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? DRR_E_NOMEM : DRR_E_CUDA, "%s: %s", #x, \
+                        cudaGetErrorString(e_));                                                     \
+    } while (0)
+
+static void free_volume(VolHost& v) {
+    if (v.tex) cudaDestroyTextureObject(v.tex);
+    if (v.arr) cudaFreeArray(v.arr);
+    cudaFree(v.dens); cudaFree(v.lab); cudaFree(v.cellc); cudaFree(v.celll);
+    v = VolHost();
+}
+
+extern "C" {
+
+const char* drr_version(void) { return "drr_b200 0.1.0 sm_100a"; }
+
+const char* drr_last_error(const drr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int drr_create(int device_id, drr_ctx** out) {
+    if (!out) return fail(nullptr, DRR_E_INVALID, "drr_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, DRR_E_CUDA, "drr_create: no CUDA device (%s); libdrr_b200 has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(nullptr, DRR_E_INVALID, "drr_create: device %d out of range [0,%d)", device_id, n);
+    CU(nullptr, cudaSetDevice(device_id));
+    drr_ctx* c = new (std::nothrow) drr_ctx();
+    if (!c) return fail(nullptr, DRR_E_NOMEM, "drr_create: out of host memory");
+    c->device = device_id;
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device_id));
+    c->n_sm = prop.multiProcessorCount;
+    CU(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 5; i++) CU(nullptr, cudaEventCreate(&c->ev[i]));
+    CU(nullptr, cudaMalloc(&c->d_samples, sizeof(unsigned long long)));
+    CU(nullptr, cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+    for (int i = 0; i < DRR_MAX_VOLUMES; i++) { c->priority[i] = 0; c->enabled[i] = 1; }
+    *out = c;
+    return DRR_OK;
+}
+
+int drr_clear_volumes(drr_ctx* c) {
+    if (!c) return DRR_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& v : c->vols) free_volume(v);
+    c->vols.clear();
+    c->priorities_set = false;
+    return DRR_OK;
+}
+
+int drr_destroy(drr_ctx* c) {
+    if (!c) return DRR_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    drr_clear_volumes(c);
+    for (void* p : c->mesh_owned) cudaFree(p);
+    cudaFree(c->d_energies); cudaFree(c->d_pdf); cudaFree(c->d_mu);
+    cudaFree(c->d_views); cudaFreeHost(c->h_views);
+    cudaFree(c->d_area); cudaFree(c->d_intensity); cudaFree(c->d_pprob); cudaFree(c->d_scratch);
+    cudaFree(c->d_minmax); cudaFree(c->d_viewsum); cudaFree(c->d_samples); cudaFree(c->d_tile_counter);
+    for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return DRR_OK;
+}
+
+int drr_set_stream(drr_ctx* c, void* s) {
+    if (!c) return DRR_E_INVALID;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return DRR_OK;
+}
+
+int drr_synchronize(drr_ctx* c) {
+    if (!c) return DRR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return DRR_OK;
+}
+
+int drr_set_spectrum(drr_ctx* c, int n_bins, int M, const float* energies, const float* pdf, const float* mu) {
+    if (!c) return DRR_E_INVALID;
+    if (n_bins <= 0 || M <= 0 || M > DRR_MAX_MATERIALS || !energies || !pdf || !mu)
+        return fail(c, DRR_E_INVALID, "drr_set_spectrum: need n_bins > 0, 1 <= n_materials <= %d and non-NULL tables", DRR_MAX_MATERIALS);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_energies); cudaFree(c->d_pdf); cudaFree(c->d_mu);
+    c->d_energies = c->d_pdf = c->d_mu = nullptr;
+    CU(c, cudaMalloc(&c->d_energies, sizeof(float) * n_bins));
+    CU(c, cudaMalloc(&c->d_pdf, sizeof(float) * n_bins));
+    CU(c, cudaMalloc(&c->d_mu, sizeof(float) * (size_t)n_bins * M));
+    CU(c, cudaMemcpy(c->d_energies, energies, sizeof(float) * n_bins, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_pdf, pdf, sizeof(float) * n_bins, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_mu, mu, sizeof(float) * (size_t)n_bins * M, cudaMemcpyHostToDevice));
+    c->n_bins = n_bins;
+    c->M = M;
+    return DRR_OK;
+}
+
+int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind, unsigned flags,
+                   int* vol_id) {
+    if (!c) return DRR_E_INVALID;
+    if (!density || !labels || ni <= 0 || nj <= 0 || nk <= 0) return fail(c, DRR_E_INVALID, "drr_add_volume: bad arguments");
+    if ((int)c->vols.size() >= DRR_MAX_VOLUMES) return fail(c, DRR_E_INVALID, "drr_add_volume: at most %d volumes", DRR_MAX_VOLUMES);
+    if (ni > 16384 || nj > 16384 || nk > 16384) return fail(c, DRR_E_INVALID, "drr_add_volume: dimension above 16384");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t n = (size_t)ni * nj * nk;
+    VolHost v;
+    v.ni = ni; v.nj = nj; v.nk = nk;
+    float* d_in = nullptr;
+    uint8_t* l_in = nullptr;
+    auto cleanup = [&]() { free_volume(v); if (mem_kind == DRR_MEM_HOST) { cudaFree(d_in); cudaFree(l_in); } };
+#define CUV(x)                                                                                                     \
+    do {                                                                                                           \
+        cudaError_t e_ = (x);                                                                                      \
+        if (e_ != cudaSuccess) {                                                                                   \
+            cleanup();                                                                                             \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? DRR_E_NOMEM : DRR_E_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+        }                                                                                                          \
+    } while (0)
+    if (mem_kind == DRR_MEM_HOST) {
+        CUV(cudaMalloc(&d_in, n * sizeof(float)));
+        CUV(cudaMalloc(&l_in, n));
+        CUV(cudaMemcpyAsync(d_in, density, n * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUV(cudaMemcpyAsync(l_in, labels, n, cudaMemcpyHostToDevice, s));
+    } else {
+        d_in = const_cast<float*>(density);
+        l_in = const_cast<uint8_t*>(labels);
+    }
+    CUV(cudaMalloc(&v.dens, n * sizeof(float)));
+    CUV(cudaMalloc(&v.lab, n));
+    dim3 tb(32, 8), tg((nk + 31) / 32, (ni + 31) / 32, nj);
+    transpose_ik_kernel<float><<<tg, tb, 0, s>>>(d_in, v.dens, ni, nj, nk);
+    transpose_ik_kernel<uint8_t><<<tg, tb, 0, s>>>(l_in, v.lab, ni, nj, nk);
+    c->launches += 2;
+    CUV(cudaGetLastError());
+    if (!(flags & 1u)) {
+        const size_t ncell = (size_t)(ni + 1) * (nj + 1) * (nk + 1);
+        CUV(cudaMalloc(&v.cellc, ncell * 2 * sizeof(float4)));
+        CUV(cudaMalloc(&v.celll, ncell * sizeof(uint2)));
+        dim3 cg((ni + 1 + 127) / 128, nj + 1, nk + 1);
+        build_cells_kernel<<<cg, 128, 0, s>>>(v.dens, v.lab, ni, nj, nk, v.cellc, v.celll);
+        c->launches += 1;
+        CUV(cudaGetLastError());
+    }
+    if (!(flags & 2u)) {
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        CUV(cudaMalloc3DArray(&v.arr, &fd, make_cudaExtent(ni, nj, nk)));
+        cudaMemcpy3DParms p = {};
+        p.srcPtr = make_cudaPitchedPtr(v.dens, (size_t)ni * sizeof(float), ni, nj);
+        p.dstArray = v.arr;
+        p.extent = make_cudaExtent(ni, nj, nk);
+        p.kind = cudaMemcpyDeviceToDevice;
+        CUV(cudaMemcpy3DAsync(&p, s));
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = v.arr;
+        cudaTextureDesc td = {};  // projector.py:189-235: clamp, linear, element type, unnormalised coordinates
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CUV(cudaCreateTextureObject(&v.tex, &rd, &td, nullptr));
+    }
+    CUV(cudaStreamSynchronize(s));
+    if (mem_kind == DRR_MEM_HOST) { cudaFree(d_in); cudaFree(l_in); }
+#undef CUV
+    c->vols.push_back(v);
+    if (vol_id) *vol_id = (int)c->vols.size() - 1;
+    return DRR_OK;
+}
+
+int drr_set_priorities(drr_ctx* c, const int* priority, const int* enabled, int n) {
+    if (!c) return DRR_E_INVALID;
+    if (n < 0 || n > DRR_MAX_VOLUMES) return fail(c, DRR_E_INVALID, "drr_set_priorities: bad volume count %d", n);
+    for (int i = 0; i < n; i++) {
+        if (priority) c->priority[i] = priority[i];
+        if (enabled) c->enabled[i] = enabled[i];
+    }
+    if (priority) c->priorities_set = true;
+    return DRR_OK;
+}
+
+int drr_set_march(drr_ctx* c, float step, int attenuate_outside, int air_index, int sampler) {
+    if (!c) return DRR_E_INVALID;
+    if (!(step > 0.0f)) return fail(c, DRR_E_INVALID, "drr_set_march: step must be positive");
+    if (sampler < 0 || sampler > 2) return fail(c, DRR_E_INVALID, "drr_set_march: unknown sampler %d", sampler);
+    c->step = step;
+    c->attenuate_outside = attenuate_outside ? 1 : 0;
+    c->air_index = air_index;
+    c->sampler = sampler;
+    return DRR_OK;
+}
+
+int drr_set_hybrid_share(drr_ctx* c, int tex_eighths) {  // tuning knob (not part of the stable ABI)
+    if (!c || tex_eighths < 0 || tex_eighths > 8) return DRR_E_INVALID;
+    c->tex_eighths = tex_eighths;
+    return DRR_OK;
+}
+
+int drr_set_mesh_buffers(drr_ctx* c, int layers, int max_hits, const float* hit_alphas, const int8_t* hit_facing,
+                         const int8_t* layer_valid, const float* additive, const int* mesh_mats, int n_mesh_mats, int mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (void* p : c->mesh_owned) cudaFree(p);
+    c->mesh_owned.clear();
+    c->hit_alphas = nullptr; c->hit_facing = nullptr; c->layer_valid = nullptr; c->additive = nullptr; c->mesh_mats = nullptr;
+    c->mesh_layers = 0; c->max_hits = 0; c->n_mesh_mats = 0;
+    if (!layer_valid && !additive) return DRR_OK;
+    if (layers <= 0 || layers > 4) return fail(c, DRR_E_INVALID, "drr_set_mesh_buffers: 1..4 mesh layers supported");
+    if (mem_kind != DRR_MEM_DEVICE)
+        return fail(c, DRR_E_INVALID, "drr_set_mesh_buffers: pass device pointers (per-batch sizes are only known to the caller)");
+    c->mesh_layers = layers; c->max_hits = max_hits; c->n_mesh_mats = n_mesh_mats;
+    c->hit_alphas = hit_alphas; c->hit_facing = hit_facing; c->layer_valid = layer_valid;
+    c->additive = additive; c->mesh_mats = mesh_mats;
+    return DRR_OK;
+}
+
+static int ensure(drr_ctx* c, void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return DRR_OK;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CU(c, cudaMalloc(p, bytes));
+    *cap = bytes;
+    return DRR_OK;
+}
+
+int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const float* src_ijk, const float* ijk_from_world,
+                float max_ray_length, unsigned post_flags, float photon_count, float intensity_upper_bound, float pixel_area_mm2,
+                uint64_t seed, float* out_intensity, float* out_pprob, float* out_area, int out_mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    if (n_views <= 0 || W <= 0 || H <= 0 || !w2i) return fail(c, DRR_E_INVALID, "drr_project: bad view / sensor arguments");
+    if (c->n_bins == 0) return fail(c, DRR_E_STATE, "drr_project: call drr_set_spectrum first");
+    const int V = (int)c->vols.size();
+    if (V > 0 && (!src_ijk || !ijk_from_world)) return fail(c, DRR_E_INVALID, "drr_project: missing per-volume pose arrays");
+    if (!out_intensity && !out_area) return fail(c, DRR_E_INVALID, "drr_project: no output requested");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t npix = (size_t)W * H;
+    const int M = c->M;
+
+    // per-view poses -> pinned staging -> device (one copy per batch instead of 5 per view, projector.py:802-831)
+    if (c->views_cap < n_views) {
+        cudaFree(c->d_views); cudaFreeHost(c->h_views);
+        c->d_views = nullptr; c->h_views = nullptr; c->views_cap = 0;
+        CU(c, cudaMalloc(&c->d_views, sizeof(ViewDev) * n_views));
+        CU(c, cudaMallocHost(&c->h_views, sizeof(ViewDev) * n_views));
+        c->views_cap = n_views;
+    }
+    for (int i = 0; i < n_views; i++) {
+        ViewDev& vd = c->h_views[i];
+        memset(&vd, 0, sizeof vd);
+        memcpy(vd.w2i, w2i + (size_t)i * 9, 36);
+        for (int v = 0; v < V; v++) {
+            memcpy(vd.src[v], src_ijk + ((size_t)i * V + v) * 3, 12);
+            memcpy(vd.ijk[v], ijk_from_world + ((size_t)i * V + v) * 12, 48);
+        }
+    }
+    CU(c, cudaEventRecord(c->ev[0], s));
+    CU(c, cudaMemcpyAsync(c->d_views, c->h_views, sizeof(ViewDev) * n_views, cudaMemcpyHostToDevice, s));
+
+    int rc;
+    if ((rc = ensure(c, (void**)&c->d_area, &c->area_cap, sizeof(float) * npix * M * n_views))) return rc;
+    if ((rc = ensure(c, (void**)&c->d_intensity, &c->int_cap, sizeof(float) * npix * n_views))) return rc;
+    if ((rc = ensure(c, (void**)&c->d_pprob, &c->pp_cap, sizeof(float) * npix * n_views))) return rc;
+    CU(c, cudaMemsetAsync(c->d_samples, 0, sizeof(unsigned long long), s));
+    CU(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), s));
+
+    MarchParams P;
+    memset(&P, 0, sizeof P);
+    for (int v = 0; v < V; v++) {
+        const VolHost& h = c->vols[v];
+        P.vol[v].dens = h.dens; P.vol[v].lab = h.lab; P.vol[v].cellc = h.cellc; P.vol[v].celll = h.celll;
+        P.vol[v].tex = h.tex; P.vol[v].ni = h.ni; P.vol[v].nj = h.nj; P.vol[v].nk = h.nk;
+        P.priority[v] = c->priorities_set ? c->priority[v] : V - 1 - v;  // projector.py:489-492
+        P.enabled[v] = c->enabled[v];
+    }
+    P.V = V; P.M = M; P.W = W; P.H = H; P.n_views = n_views;
+    P.step = c->step; P.max_ray_length = max_ray_length;
+    P.attenuate_outside = c->attenuate_outside; P.air_index = c->air_index;
+    P.mesh_layers = c->mesh_layers; P.max_hits = c->max_hits; P.n_mesh_mats = c->n_mesh_mats;
+    P.hit_alphas = c->hit_alphas; P.hit_facing = c->hit_facing; P.layer_valid = c->layer_valid;
+    P.additive = c->additive; P.mesh_mats = c->mesh_mats;
+    P.views = c->d_views; P.area = c->d_area; P.sample_count = c->d_samples; P.tile_counter = c->d_tile_counter;
+
+    const bool meshes = c->layer_valid || c->additive;
+    bool single = (V == 1) && !meshes && !c->attenuate_outside && M <= 8;
+    if (single) {
+        const VolHost& h = c->vols[0];
+        int sampler = c->sampler;
+        if (sampler != DRR_SAMPLER_TEX && !h.cellc) sampler = h.tex ? DRR_SAMPLER_TEX : -1;
+        if (sampler != DRR_SAMPLER_ALU && !h.tex) sampler = h.cellc ? DRR_SAMPLER_ALU : -1;
+        if (sampler < 0) return fail(c, DRR_E_STATE, "drr_project: volume 0 has neither cell records nor a texture");
+        P.tex_eighths = sampler == DRR_SAMPLER_ALU ? 0 : (sampler == DRR_SAMPLER_TEX ? 8 : c->tex_eighths);
+    }
+    CU(c, cudaEventRecord(c->ev[1], s));
+    if (V == 0) {
+        CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
+    } else if (single) {
+        int occ = drr_march_single_occupancy(M);
+        if (occ < 1) occ = 1;
+        int grid = c->n_sm * occ;  // persistent: every resident warp pulls 8x4-pixel tiles from the queue
+        CU(c, drr_launch_march_single(P, grid, s));
+        c->launches += 1;
+    } else {
+        if (V > 4 || M > 8) return fail(c, DRR_E_INVALID, "drr_project: the general kernel supports up to 4 volumes / 8 materials");
+        for (int v = 0; v < V; v++)
+            if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_project: volume %d has no raw arrays", v);
+        CU(c, drr_launch_march_general(P, s));
+        c->launches += 1;
+    }
+    CU(c, cudaEventRecord(c->ev[2], s));
+
+    if (out_intensity) {
+        CU(c, drr_launch_spectral(c->d_area, c->n_bins, M, c->d_energies, c->d_pdf, c->d_mu, npix, n_views, c->d_intensity, c->d_pprob,
+                                  c->n_sm, s));
+        c->launches += 1;
+        if (post_flags & DRR_POST_COLLECTED) {
+            if ((rc = ensure(c, (void**)&c->d_scratch, &c->scratch_cap, sizeof(float) * npix * n_views))) return rc;
+            if (c->minmax_cap < n_views) {
+                cudaFree(c->d_minmax); cudaFree(c->d_viewsum);
+                CU(c, cudaMalloc(&c->d_minmax, sizeof(unsigned) * 2 * n_views));
+                CU(c, cudaMalloc(&c->d_viewsum, sizeof(double) * n_views));
+                c->minmax_cap = n_views;
+            }
+            CU(c, drr_launch_collected(c->d_intensity, c->d_scratch, c->d_viewsum, c->d_views, W, H, n_views, photon_count, pixel_area_mm2, s));
+            c->launches += 2;
+        }
+        if (post_flags & DRR_POST_NOISE) {
+            if ((rc = ensure(c, (void**)&c->d_scratch, &c->scratch_cap, sizeof(float) * npix * n_views))) return rc;
+            CU(c, drr_launch_noise(c->d_intensity, c->d_pprob, c->d_scratch, W, H, n_views, photon_count, seed, s));
+            c->launches += 2;
+        }
+        if (post_flags & DRR_POST_CLIP) {
+            CU(c, drr_launch_clip(c->d_intensity, npix * n_views, intensity_upper_bound, s));
+            c->launches += 1;
+        }
+        if (post_flags & DRR_POST_NEGLOG) {
+            if (c->minmax_cap < n_views) {
+                cudaFree(c->d_minmax); cudaFree(c->d_viewsum);
+                CU(c, cudaMalloc(&c->d_minmax, sizeof(unsigned) * 2 * n_views));
+                CU(c, cudaMalloc(&c->d_viewsum, sizeof(double) * n_views));
+                c->minmax_cap = n_views;
+            }
+            CU(c, drr_launch_neglog(c->d_intensity, npix, n_views, c->d_minmax, 0.01f, s));
+            c->launches += 2;
+        }
+    }
+    CU(c, cudaEventRecord(c->ev[3], s));
+    const cudaMemcpyKind kind = out_mem_kind == DRR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (out_intensity) CU(c, cudaMemcpyAsync(out_intensity, c->d_intensity, sizeof(float) * npix * n_views, kind, s));
+    if (out_pprob && out_intensity) CU(c, cudaMemcpyAsync(out_pprob, c->d_pprob, sizeof(float) * npix * n_views, kind, s));
+    if (out_area) CU(c, cudaMemcpyAsync(out_area, c->d_area, sizeof(float) * npix * M * n_views, kind, s));
+    CU(c, cudaMemcpyAsync(&c->last_samples, c->d_samples, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->ev[4], s));
+    CU(c, cudaStreamSynchronize(s));
+    CU(c, cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]));
+    CU(c, cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]));
+    CU(c, cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[4]));
+    return DRR_OK;
+}
+
+int drr_last_timing(const drr_ctx* c, float* ms3) {
+    if (!c || !ms3) return DRR_E_INVALID;
+    ms3[0] = c->last_ms[0]; ms3[1] = c->last_ms[1]; ms3[2] = c->last_ms[2];
+    return DRR_OK;
+}
+
+int drr_last_sample_count(const drr_ctx* c, unsigned long long* samples) {
+    if (!c || !samples) return DRR_E_INVALID;
+    *samples = c->last_samples;
+    return DRR_OK;
+}
+
+int drr_launch_count(const drr_ctx* c, unsigned long long* launches) {
+    if (!c || !launches) return DRR_E_INVALID;
+    *launches = c->launches;
+    return DRR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+"""``Projector`` -- drop-in for ``deepdrr.Projector`` on the projection path, backed by libdrr_b200.so.
+
+Mirrors the reference class (deepdrr/projector/projector.py:395-1774): same constructor arguments
+and defaults (:398-422), ``initialize`` / ``free`` / context manager (:1395, :1719, :1766-1771),
+``project`` / ``__call__`` over any number of camera projections (:655-707, :1773), the ``volume``,
+``output_size``, ``camera_intrinsics`` and ``source_to_detector_distance`` properties (:584-625) and the
+same exceptions.  The host side stays Python/NumPy; every GPU step goes through the C ABI in
+``include/drr_b200.h`` via ctypes.  No CuPy / PyCUDA / Triton, and no CPU fallback.
+
+Differences that do not change results: views are projected as one batch (one pose upload, one
+launch sequence, one download) instead of the reference's per-view loop, and neglog / noise / clip
+run on the GPU instead of on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import math
+import warnings
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib, geo, vol
+from .material import Material
+from .scene import default_priorities, material_universe, remap_labels
+from .spectral_data import get_spectrum, spectrum_tables
+from .material import absorb_coef_table
+
+log = logging.getLogger(__name__)
+
+
+class DeprecationError(Exception):
+    """Same role as deepdrr.projector.projector.DeprecationError (raised for removed features)."""
+
+
+def _listify(x):
+    if isinstance(x, (list, tuple)):
+        return list(x)
+    return [x]
+
+
+class Projector(object):
+    volumes: List[vol.Volume]
+
+    def __init__(
+        self,
+        volume,
+        priorities: Optional[List[int]] = None,
+        camera_intrinsics: Optional[geo.CameraIntrinsicTransform] = None,
+        device=None,
+        step: float = 0.1,
+        mode: str = "linear",
+        spectrum: Union[np.ndarray, str] = "90KV_AL40",
+        add_scatter: Optional[bool] = None,
+        scatter_num: int = 0,
+        add_noise: bool = False,
+        photon_count: int = 10000,
+        threads: int = 8,
+        max_block_index: int = 65535,
+        collected_energy: bool = False,
+        neglog: bool = True,
+        intensity_upper_bound: Optional[float] = None,
+        attenuate_outside_volume: bool = False,
+        source_to_detector_distance: float = -1,
+        carm=None,
+        max_mesh_hits=32,
+        mesh_layers=2,
+        cuda_device_id=None,
+        sampler: str = "hybrid",
+        noise_seed: Optional[int] = None,
+    ) -> None:
+        """See the reference docstring (projector.py:423-454).  Extra, optional arguments:
+
+        sampler: "hybrid" (default), "alu" or "tex" -- which units fetch the density (same arithmetic).
+        noise_seed: seed of the Philox stream used by ``add_noise`` (the reference uses unseeded NumPy).
+        """
+        self.cuda_device_id = cuda_device_id
+        self.mesh_layers = mesh_layers
+
+        volume = _listify(volume)
+        self.volumes = []
+        self.priorities = []
+        self.primitives = []
+        self.meshes = []
+        for _vol in volume:
+            if isinstance(_vol, vol.Volume) or (hasattr(_vol, "data") and hasattr(_vol, "materials")):
+                self.volumes.append(_vol)
+            elif hasattr(_vol, "mesh") or hasattr(_vol, "triangles"):
+                self.meshes.append(_vol)
+            else:
+                raise ValueError(f"unrecognized Renderable type: {type(_vol)}.")
+        self.mesh_additive_enabled = len(self.meshes) > 0
+        if self.meshes:
+            raise NotImplementedError("mesh rendering (CUDA ray-triangle hit intervals) is not wired into Projector yet")
+
+        if priorities is None:
+            self.priorities = default_priorities(len(self.volumes))
+        else:
+            for prio in priorities:
+                assert isinstance(prio, int), "missing priority, or priority is not an integer"
+                assert (0 <= prio) and (prio < len(volume)), "invalid priority outside range [0, NUM_VOLUMES)"
+                self.priorities.append(prio)
+        assert len(self.volumes) == len(self.priorities)
+
+        if carm is not None:
+            warnings.warn("carm is deprecated, use device instead", DeprecationWarning)
+            self.device = carm
+        else:
+            self.device = device
+
+        self._camera_intrinsics = camera_intrinsics
+        self.step = float(step)
+        self.mode = mode  # accepted and ignored, as in the reference
+        self.spectrum_arr = get_spectrum(spectrum)
+        self._source_to_detector_distance = source_to_detector_distance
+
+        if add_scatter is not None:
+            log.warning("add_scatter is deprecated. Set scatter_num instead.")
+            if scatter_num != 0:
+                raise ValueError("Only set scatter_num.")
+            self.scatter_num = 1e7 if add_scatter else 0
+        elif scatter_num < 0:
+            raise ValueError(f"scatter_num must be non-negative.")
+        else:
+            self.scatter_num = scatter_num
+        if self.scatter_num > 0 and self.device is None:
+            raise ValueError("Must provide device to simulate scatter.")
+        if self.scatter_num > 0:
+            raise DeprecationError("Scatter is deprecated.")
+
+        self.add_noise = add_noise
+        self.photon_count = photon_count
+        self.threads = threads  # no effect on results (Q8)
+        self.max_block_index = max_block_index
+        self.collected_energy = collected_energy
+        self.neglog = neglog
+        self.intensity_upper_bound = intensity_upper_bound
+
+        self.max_mesh_hits = max_mesh_hits
+        if self.max_mesh_hits < 4 or self.max_mesh_hits % 4 != 0:
+            raise ValueError("max_mesh_depth must be a multiple of 4 and >= 4")
+
+        self.all_materials = material_universe(self.volumes, [], attenuate_outside_volume)
+        if attenuate_outside_volume:
+            assert "air" in self.all_materials
+            air_index = self.all_materials.index("air")
+        else:
+            air_index = 0
+        self.air_index = air_index
+        self.attenuate_outside_volume = attenuate_outside_volume
+
+        for mat in self.all_materials:
+            try:
+                Material.from_string(mat)
+            except AttributeError:
+                raise ValueError(f"Material {mat} not found in material database. Please check the material name.")
+
+        if sampler not in ("hybrid", "alu", "tex"):
+            raise ValueError(f"unknown sampler {sampler!r}")
+        self.sampler = sampler
+        self.noise_seed = noise_seed
+        self._noise_calls = 0
+
+        self.output_shape = None
+        self.initialized = False
+        self._h = None
+        self.max_ray_length = None
+
+    # ------------------------------------------------------------------ properties (:584-625)
+    @property
+    def source_to_detector_distance(self) -> float:
+        if self.device is not None:
+            return self.device.source_to_detector_distance
+        return self._source_to_detector_distance
+
+    @property
+    def camera_intrinsics(self):
+        if self.device is not None:
+            return self.device.camera_intrinsics
+        elif self._camera_intrinsics is not None:
+            return self._camera_intrinsics
+        raise RuntimeError("No device provided. Set the device attribute by passing `device=<device>` to the constructor.")
+
+    @camera_intrinsics.setter
+    def camera_intrinsics(self, value):
+        if self.device is not None:
+            raise RuntimeError("Cannot set camera intrinsics when a device is provided. Use the device's camera_intrinsics instead.")
+        elif isinstance(value, geo.CameraIntrinsicTransform) or hasattr(value, "sensor_size"):
+            self._camera_intrinsics = value
+        else:
+            raise TypeError(f"Expected geo.CameraIntrinsicTransform, got {type(value)} instead.")
+
+    @property
+    def volume(self):
+        if len(self.volumes) != 1:
+            raise AttributeError("projector contains multiple volumes. Access them with `projector.volumes[i]`")
+        return self.volumes[0]
+
+    @property
+    def output_size(self) -> int:
+        return int(np.prod(self.output_shape))
+
+    # ------------------------------------------------------------------ lifecycle
+    def initialize(self):
+        """Create the GPU handle and upload volumes, labels and tables (reference: :1395-1717)."""
+        if self.initialized:
+            raise RuntimeError("Close projector before initializing again.")
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.drr_create(int(self.cuda_device_id or 0), ctypes.byref(h)))
+        self._h = h
+        try:
+            energies, pdf = spectrum_tables(self.spectrum_arr)
+            mu = absorb_coef_table(self.all_materials, energies)
+            self._energies, self._pdf, self._mu = energies, pdf, mu
+            _lib.check(lib.drr_set_spectrum(h, len(energies), len(self.all_materials), _lib.ptr(energies), _lib.ptr(pdf),
+                                            _lib.ptr(mu)), h)
+            for _vol in self.volumes:
+                dens = np.ascontiguousarray(np.asarray(_vol.data), dtype=np.float32)
+                labels = np.ascontiguousarray(remap_labels(_vol, self.all_materials))
+                vid = ctypes.c_int(-1)
+                _lib.check(lib.drr_add_volume(h, _lib.ptr(dens), _lib.ptr(labels), dens.shape[0], dens.shape[1], dens.shape[2],
+                                              _lib.MEM_HOST, 0, ctypes.byref(vid)), h)
+            sampler = {"alu": _lib.SAMPLER_ALU, "tex": _lib.SAMPLER_TEX, "hybrid": _lib.SAMPLER_HYBRID}[self.sampler]
+            _lib.check(lib.drr_set_march(h, self.step, int(self.attenuate_outside_volume), int(self.air_index), sampler), h)
+        except Exception:
+            lib.drr_destroy(h)
+            self._h = None
+            raise
+        self.output_shape = tuple(self.camera_intrinsics.sensor_size) if (self.device is not None or self._camera_intrinsics is not None) else None
+        self.initialized = True
+
+    def free(self):
+        """Free the GPU handle (reference: :1719-1764)."""
+        if self.initialized and self._h is not None:
+            _lib.load().drr_destroy(self._h)
+            self._h = None
+        self.initialized = False
+
+    def __enter__(self):
+        self.initialize()
+        return self
+
+    def __exit__(self, type, value, tb):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __call__(self, *args, **kwargs):
+        return self.project(*args, **kwargs)
+
+    # ------------------------------------------------------------------ projection
+    def _prepare_project(self, camera_projections):
+        """Reference: :628-652."""
+        if not self.initialized:
+            raise RuntimeError("Projector has not been initialized.")
+        if not camera_projections and self.device is None:
+            raise ValueError("must provide a camera projection object to the projector, unless imaging device (e.g. CArm) is provided")
+        elif not camera_projections and self.device is not None:
+            camera_projections = [self.device.get_camera_projection()]
+            self.max_ray_length = math.sqrt(self.device.source_to_detector_distance ** 2 + self.device.detector_height ** 2
+                                            + self.device.detector_width ** 2)
+        else:
+            self.max_ray_length = self.source_to_detector_distance * 4
+        return list(camera_projections)
+
+    def project(self, *camera_projections, max_ray_length: Optional[float] = None) -> np.ndarray:
+        """Project every given view; returns ``[H, W]`` for one view, ``[N, H, W]`` otherwise (float32).
+
+        Reference: :655-707.  ``max_ray_length`` (extra) overrides the value derived at :641-650.
+        """
+        camera_projections = self._prepare_project(camera_projections)
+        if max_ray_length is not None:
+            self.max_ray_length = float(max_ray_length)
+        images = self._project_batch(camera_projections, want="intensity")
+        if images.shape[0] == 1:
+            return images[0]
+        return images
+
+    def project_line_integrals(self, *camera_projections, max_ray_length: Optional[float] = None) -> np.ndarray:
+        """Extra: per-material area densities ``[N, M, H, W]`` in g/cm^2 (project_kernel.cu:565-584),
+        materials in ``self.all_materials`` order."""
+        camera_projections = self._prepare_project(camera_projections)
+        if max_ray_length is not None:
+            self.max_ray_length = float(max_ray_length)
+        return self._project_batch(camera_projections, want="area")
+
+    def _pose_arrays(self, camera_projections):
+        n, V = len(camera_projections), len(self.volumes)
+        w2i = np.zeros((n, 9), dtype=np.float32)
+        src = np.zeros((n, max(V, 1), 3), dtype=np.float32)
+        ijk = np.zeros((n, max(V, 1), 12), dtype=np.float32)
+        for i, proj in enumerate(camera_projections):
+            a, b, c = geo.pose_arrays(proj, self.volumes)
+            w2i[i] = a
+            if V:
+                src[i], ijk[i] = b, c
+        return w2i, src, ijk
+
+    def _project_batch(self, camera_projections, want="intensity", out=None, raw=False):
+        lib, h = _lib.load(), self._h
+        n = len(camera_projections)
+        sizes = {tuple(p.intrinsic.sensor_size) for p in camera_projections}
+        if len(sizes) != 1:
+            raise ValueError("all camera projections of one call must share the sensor size")
+        W, H = sizes.pop()
+        self.output_shape = (W, H)
+        w2i, src, ijk = self._pose_arrays(camera_projections)
+        V = len(self.volumes)
+        pr = np.ascontiguousarray(self.priorities, dtype=np.int32)
+        en = np.ascontiguousarray([1 if getattr(v, "enabled", True) else 0 for v in self.volumes], dtype=np.int32)
+        _lib.check(lib.drr_set_priorities(h, _lib.ptr(pr) if V else None, _lib.ptr(en) if V else None, V), h)
+
+        flags = 0
+        if want == "intensity" and not raw:
+            if self.collected_energy:
+                flags |= _lib.POST_COLLECTED
+            if self.add_noise:
+                flags |= _lib.POST_NOISE
+            if self.intensity_upper_bound is not None:
+                flags |= _lib.POST_CLIP
+            if self.neglog:
+                flags |= _lib.POST_NEGLOG
+        pixel_area = 1.0
+        if flags & _lib.POST_COLLECTED:
+            k = camera_projections[0].intrinsic
+            pixel_area = (self.source_to_detector_distance / k.fx) * (self.source_to_detector_distance / k.fy)
+        seed = (self.noise_seed if self.noise_seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFF) + self._noise_calls
+        self._noise_calls += 1
+        M = len(self.all_materials)
+        if want == "intensity":
+            images = out if out is not None else np.empty((n, H, W), dtype=np.float32)
+            mem = _lib.MEM_DEVICE if hasattr(images, "data_ptr") and images.is_cuda else _lib.MEM_HOST
+            _lib.check(lib.drr_project(h, n, W, H, _lib.ptr(w2i), _lib.ptr(src), _lib.ptr(ijk), float(self.max_ray_length), flags,
+                                       float(self.photon_count), float(self.intensity_upper_bound or 0.0), float(pixel_area),
+                                       seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(images), None, None, mem), h)
+            return images
+        area = out if out is not None else np.empty((n, M, H, W), dtype=np.float32)
+        mem = _lib.MEM_DEVICE if hasattr(area, "data_ptr") and area.is_cuda else _lib.MEM_HOST
+        _lib.check(lib.drr_project(h, n, W, H, _lib.ptr(w2i), _lib.ptr(src), _lib.ptr(ijk), float(self.max_ray_length), 0, 0.0, 0.0, 1.0,
+                                   0, None, None, _lib.ptr(area), mem), h)
+        return area
+
+    # ------------------------------------------------------------------ introspection used by bench / tests
+    def last_timing_ms(self):
+        t = (ctypes.c_float * 3)()
+        _lib.check(_lib.load().drr_last_timing(self._h, t), self._h)
+        return {"march": t[0], "spectral_post": t[1], "total": t[2]}
+
+    def last_sample_count(self) -> int:
+        s = ctypes.c_ulonglong(0)
+        _lib.check(_lib.load().drr_last_sample_count(self._h, ctypes.byref(s)), self._h)
+        return int(s.value)
+
+    def launch_count(self) -> int:
+        s = ctypes.c_ulonglong(0)
+        _lib.check(_lib.load().drr_launch_count(self._h, ctypes.byref(s)), self._h)
+        return int(s.value)
+
+    def set_hybrid_share(self, tex_eighths: int):
+        _lib.check(_lib.load().drr_set_hybrid_share(self._h, int(tex_eighths)), self._h)
+
+    def project_over_carm_range(self, *a, **k):
+        raise DeprecationError("project_over_carm_range is deprecated. See README for alternatives.")

@@ -1,0 +1,127 @@
+/* drr_b200.h -- C ABI of libdrr_b200.so, the B200-native (sm_100a) DRR projection library.
+ *
+ * This is the drop-in boundary for the projection path of arcadelab/deepdrr.  The reference has no
+ * stable FFI for this path: its "ABI" is the positional CuPy RawKernel launch of `projectKernel`
+ * (deepdrr/projector/projector.py:718-774, prototype deepdrr/projector/project_kernel.cu:136-181)
+ * plus the texture/array set-up in `Projector.initialize` (projector.py:1395-1717).  Each entry point
+ * below names the reference code it replaces.  Plain pointers and sizes only; no torch / CuPy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DRR_E_* code; drr_last_error() gives text.
+ *   - one handle per GPU; a handle is not thread-safe; all work of a handle runs on its own stream
+ *     unless a stream is passed to drr_set_stream().
+ *   - "mem kind": DRR_MEM_HOST (pageable or pinned host pointer) or DRR_MEM_DEVICE (device pointer
+ *     on the handle's GPU, e.g. torch.Tensor.data_ptr()).
+ *   - volumes arrive as the reference holds them on the host: float32 density [Ni][Nj][Nk] and
+ *     uint8 labels [Ni][Nj][Nk] already remapped to the global material index
+ *     (projector.py:1499-1509), C order (k fastest).
+ *   - images leave in the orientation Projector.project returns: [view][H][W] float32
+ *     (projector.py:786-792 does the (W,H)->(H,W) swap on the host; here the kernel writes it).
+ */
+#ifndef DRR_B200_H
+#define DRR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRR_MAX_VOLUMES 8
+#define DRR_MAX_MATERIALS 16
+
+#define DRR_OK 0
+#define DRR_E_INVALID (-1)   /* bad argument / unsupported configuration  -> ValueError   */
+#define DRR_E_CUDA (-2)      /* CUDA runtime failure                       -> RuntimeError */
+#define DRR_E_STATE (-3)     /* call order (e.g. project before volumes)   -> RuntimeError */
+#define DRR_E_NOMEM (-4)     /* device allocation failed                   -> MemoryError  */
+
+#define DRR_MEM_HOST 0
+#define DRR_MEM_DEVICE 1
+
+/* density sampling back-end of the ray march (all three give the reference's arithmetic) */
+#define DRR_SAMPLER_ALU 0     /* texture-unit arithmetic emulated on the SIMT pipes from cell records */
+#define DRR_SAMPLER_TEX 1     /* hardware tex3D fetch (the reference's own path, projector.py:116-257) */
+#define DRR_SAMPLER_HYBRID 2  /* warps split between the two so TEX units and FMA pipes run together */
+
+/* output post-processing flags for drr_project (projector.py:691-702) */
+#define DRR_POST_NEGLOG 1u      /* utils.neglog: -log(I + min(I) + 0.01), min-max to [0,1]          */
+#define DRR_POST_NOISE 2u       /* analytic_generators.add_noise: Poisson shot noise + 3x3 blur      */
+#define DRR_POST_CLIP 4u        /* np.clip(images, None, intensity_upper_bound)                      */
+#define DRR_POST_COLLECTED 8u   /* _calculate_collected_energy_per_pixel (projector.py:833-853)      */
+
+typedef struct drr_ctx drr_ctx;
+
+/* Replaces: cupy.cuda.Device(id).__enter__() + EGL/context set-up (projector.py:1410-1421). */
+int drr_create(int device_id, drr_ctx** out);
+/* Replaces: Projector.free (projector.py:1719-1764).  Frees every device allocation of the handle. */
+int drr_destroy(drr_ctx* ctx);
+/* Text of the last error of this handle (or of the failed drr_create when ctx == NULL). */
+const char* drr_last_error(const drr_ctx* ctx);
+/* Run the handle's work on a caller-owned cudaStream_t (0 = the handle's own stream). */
+int drr_set_stream(drr_ctx* ctx, void* cuda_stream);
+
+/* Replaces: energies_gpu / pdf_gpu / absorption_coef_table_gpu uploads (projector.py:1659-1686).
+ * energies_keV[n_bins], pdf[n_bins], mu_over_rho[n_bins * n_materials] (index bin * M + m). */
+int drr_set_spectrum(drr_ctx* ctx, int n_bins, int n_materials, const float* energies_keV, const float* pdf,
+                     const float* mu_over_rho);
+
+/* Replaces: per-volume create_cuda_texture for density (linear) and labels (point)
+ * (projector.py:1463-1546, 116-257).  Builds on the device, from one upload of the raw arrays:
+ * the [k][j][i] density/label arrays, the 3-D CUDA array + texture object, and the per-cell records
+ * the ALU sampler marches over.  Returns the volume index in *vol_id (order = kernel volume order).
+ * flags: bit0 = skip cell records (TEX-only handle), bit1 = skip texture (ALU-only handle). */
+int drr_add_volume(drr_ctx* ctx, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind,
+                   unsigned flags, int* vol_id);
+/* Drop all volumes (keeps spectrum).  Replaces the texture teardown in Projector.free. */
+int drr_clear_volumes(drr_ctx* ctx);
+
+/* Replaces: priorities_gpu / volume_enabled_gpu (projector.py:1606-1611, 674-675). */
+int drr_set_priorities(drr_ctx* ctx, const int* priority, const int* enabled, int n_volumes);
+
+/* Ray-march options: step (world mm; projector.py:723), attenuate_outside_volume + air_index
+ * (projector.py:554-568, -D ATTENUATE_OUTSIDE_VOLUME / AIR_INDEX), sampler = DRR_SAMPLER_*. */
+int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int air_index, int sampler);
+
+/* Tuning knob of DRR_SAMPLER_HYBRID: how many of every 8 warps fetch density through the texture
+ * unit (the rest emulate it on the FMA pipes).  0..8, default 3. */
+int drr_set_hybrid_share(drr_ctx* ctx, int tex_eighths);
+
+/* Mesh inputs of projectKernel (project_kernel.cu:172-177, 363-375, 498-517, 569-579), per view,
+ * device or host pointers; NULL disables.  Produced by drr_mesh_* (ray-triangle) or by the caller.
+ *   hit_alphas  [n_views][layers][H*W][max_hits] f32, hit_facing same shape i8,
+ *   layer_valid [layers] i8, additive [n_views][layers][n_mesh_mats][H*W][2] f32, mesh_mats [n_mesh_mats]. */
+int drr_set_mesh_buffers(drr_ctx* ctx, int layers, int max_hits, const float* hit_alphas, const int8_t* hit_facing,
+                         const int8_t* layer_valid, const float* additive, const int* mesh_mats, int n_mesh_mats,
+                         int mem_kind);
+
+/* Replaces: the per-view loop of Projector.project -> _render_single (projector.py:679-685, 709-800):
+ * _update_object_locations uploads (802-831), the projectKernel launch (770-774), the two D2H copies
+ * and swapaxes (786-792) and the host post-processing (691-702), for a whole batch of views.
+ *   world_from_index [n_views][9], source_ijk [n_views][V][3], ijk_from_world [n_views][V][12]: host f32.
+ *   out_intensity / out_photon_prob: [n_views][H][W] f32 (out_photon_prob may be NULL);
+ *   out_area: [n_views][M][H][W] f32 per-material area densities in g/cm^2 (may be NULL).
+ *   post_flags: DRR_POST_*; photon_count / intensity_upper_bound / seed used by the flags that need them. */
+int drr_project(drr_ctx* ctx, int n_views, int W, int H, const float* world_from_index, const float* source_ijk,
+                const float* ijk_from_world, float max_ray_length, unsigned post_flags, float photon_count,
+                float intensity_upper_bound, float pixel_area_mm2, uint64_t seed, float* out_intensity,
+                float* out_photon_prob, float* out_area, int out_mem_kind);
+
+/* Kernel-only timing of the last drr_project (CUDA events on the handle's stream), ms:
+ * [0] ray march, [1] spectral/post kernels, [2] whole call incl. copies. */
+int drr_last_timing(const drr_ctx* ctx, float* ms3);
+/* Sum over the last batch of max(num_steps, 0) (x volumes traced) -- SURVEY.md 8(d) "S_view". */
+int drr_last_sample_count(const drr_ctx* ctx, unsigned long long* samples);
+/* Number of kernels this library launched since the handle was created. */
+int drr_launch_count(const drr_ctx* ctx, unsigned long long* launches);
+/* Block until all work of the handle has finished. */
+int drr_synchronize(drr_ctx* ctx);
+
+/* Library / build info: "drr_b200 <version> sm_100a". */
+const char* drr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRR_B200_H */
