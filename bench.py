@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the projection hot path (BASELINE.json metric: DRRs/s, 512x512x400 CT -> 1536^2 detector).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--views-per-step B]
+
+One "step" = one batch of B views of BASELINE config 2 (synthetic 512x512x400 thorax CT, 3 materials,
+120 kV spectrum, random MobileCArm poses, 1536^2 detector) per rank.  N > 1: one process per GPU
+(torchrun), every rank holds a replica of the volume and projects its own B views per step -- no
+data-path collective; weak scaling.  Prints ONE JSON line on rank 0.
+
+value  = views / s with volumes resident in HBM and images left in device memory (CUDA events on the
+         stream the kernels run on, max over ranks).
+e2e    = same through the public API call a user makes (Projector.project on host pose objects ->
+         host images): per-view pose arrays H2D, kernels, images D2H into pinned memory, inside the
+         timed region.
+--impl reference times the reference's own unmodified CUDA kernel (oracle/_ref, compiled from
+/root/reference by oracle/Makefile) driven the way the reference's Python drives it: per view five
+small H2D uploads, one launch, two blocking D2H copies, two host transposes, host neglog
+(projector.py:679-702, 786-831).  The reference has no CPU implementation of this path; if oracle/_ref
+is absent the CPU oracle port is timed instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE, SPACING = (512, 512, 400), (0.8, 0.8, 1.0)
+SPECTRUM = "120KV_AL43"
+STEP_MM = 0.1
+WORKLOAD = "C2: synthetic 512x512x400 CT, 3 materials, 120KV_AL43, random MobileCArm poses, 1536x1536 detector, step 0.1 mm"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def _dist_setup(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif n_gpus > 1:
+        raise SystemExit("launch with torchrun for --gpus > 1")
+    return rank, world, local
+
+
+def _max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _barrier(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the march kernel from the committed ncu capture of this command, if any."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_ncu.json")))
+        return j.get("march_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_baseline_port(volume, st, carm, pose, crop=256):
+    """The CPU oracle (oracle/drr_oracle.c, OpenMP over all host cores) on a centred crop of one C2 view."""
+    from deepdrr_b200 import geo
+    from oracle import cpu_oracle
+
+    cores = os.cpu_count() or 1
+    W = H = 1536
+    u0 = (W - crop) // 2
+    w2i, src, ijk = geo.pose_arrays(pose, [volume])
+    t0 = time.perf_counter()
+    r = cpu_oracle.project([volume.data], st.labels, st.M, W, H, STEP_MM, w2i, src, ijk, carm.max_ray_length, st.energies, st.pdf, st.mu,
+                           u0=u0, v0=u0, sub=1, Ws=crop, Hs=crop, want_area=False, want_steps=True, nthreads=cores)
+    dt = time.perf_counter() - t0
+    rays_per_s = crop * crop / dt
+    return {"value": rays_per_s / (W * H), "unit": "DRRs/s", "cores": cores, "kind": "port",
+            "sample": f"{crop}x{crop} centred pixel crop of one C2 view ({int(r.steps.sum()):d} ray steps, {dt:.1f} s), extrapolated per ray to 1536x1536",
+            "rays_per_s": rays_per_s}
+
+
+def run_ours(args):
+    import torch
+
+    from deepdrr_b200 import Projector, geo, phantoms
+    from deepdrr_b200.scene import SceneTables
+
+    rank, world, local = _dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    B = args.views_per_step
+    carm = phantoms.MobileCArmGeometry()
+    W, H = carm.sensor_width, carm.sensor_height
+    volume = phantoms.thorax_volume(SHAPE, SPACING)
+    n_pose = 1000
+    poses = phantoms.c2_poses(n_pose, seed=1, carm=carm)
+    p = Projector(volume, spectrum=SPECTRUM, step=STEP_MM, neglog=True, camera_intrinsics=carm.camera_intrinsics,
+                  source_to_detector_distance=carm.source_to_detector_distance, cuda_device_id=local, sampler=args.sampler)
+    p.initialize()
+    stream = torch.cuda.current_stream()
+    p.set_stream(stream.cuda_stream)
+    p.max_ray_length = carm.max_ray_length
+
+    def step_poses(s):
+        base = (s * world + rank) * B
+        return [poses[(base + i) % n_pose] for i in range(B)]
+
+    # ---- device-resident throughput ("value") ------------------------------------------------------
+    out_dev = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+    arrays = [p._pose_arrays(step_poses(s)) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        p._run(*arrays[s], W, H, "intensity", out_dev, False, None)
+    launches0 = p.launch_count()
+    clocks = ClockSampler(local)
+    _barrier(world)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    march_ms, samples = [], 0
+    e0.record(stream)
+    for s in range(args.warmup, args.warmup + args.steps):
+        p._run(*arrays[s], W, H, "intensity", out_dev, False, None)
+        march_ms.append(p.last_timing_ms()["march"])
+        samples += p.last_sample_count()
+    e1.record(stream)
+    _barrier(world)
+    dev_ms = _max_over_ranks(e0.elapsed_time(e1), world)
+    launches = p.launch_count() - launches0
+    total_views = B * args.steps * world
+    value = total_views / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API ("e2e") -------------------------------------------------
+    pinned = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    out_host = pinned.numpy()
+    for s in range(min(args.warmup, 2)):
+        p._project_batch(step_poses(s), want="intensity", out=out_host)
+    _barrier(world)
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for s in range(args.warmup, args.warmup + args.steps):
+        p.max_ray_length = carm.max_ray_length
+        img = p._project_batch(step_poses(s), want="intensity", out=out_host)  # what Projector.project does, into pinned memory
+        checksum += float(img[0, H // 2, W // 2])
+    _barrier(world)
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = total_views / e2e_s
+    clk = clocks.stop() if rank == 0 else None
+    h2d = B * (9 + 3 + 12) * 4
+    d2h = B * H * W * 4
+
+    # ---- roofline of the dominant kernel (ray march) ------------------------------------------------
+    peaks, peak_src = _peaks()
+    bytes_view = SHAPE[0] * SHAPE[1] * SHAPE[2] * 5 + W * H * 8          # 543 162 368 B
+    avg_march_s = float(np.mean(march_ms)) * 1e-3
+    achieved = bytes_view * B / avg_march_s / 1e9
+    samples_per_s = _sum_over_ranks(samples / (sum(march_ms) * 1e-3), world)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": _ncu_traffic(), "kernel": "march_warp_kernel", "peak_source": peak_src,
+                "note": "the march is a cache-resident gather (issue / TEX bound), so the HBM fraction is small by construction (SURVEY.md 8(d)); "
+                        "binding-resource figures are in 'binding'"}
+    binding = {"ray_steps_per_s": samples_per_s, "march_ms_per_view": float(np.mean(march_ms)) / B,
+               "steps_per_view": samples / (B * args.steps), "gather_GBps_at_40B_per_step": samples_per_s * 40 / 1e9}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        st = SceneTables([volume], SPECTRUM)
+        cpu = cpu_baseline_port(volume, st, carm, poses[0])
+    p.free()
+    if rank == 0:
+        line = {"metric": "DRRs/s", "value": value, "unit": "DRRs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "rays_per_s": value * W * H,
+                "config": {"workload": WORKLOAD, "views_per_step_per_gpu": B, "sensor": [W, H], "volume": list(SHAPE), "step_mm": STEP_MM,
+                           "sampler": args.sampler, "cache": "inputs larger than L2 (4.2 GB of cell records + 0.5 GB volume per GPU)",
+                           "parallelism": f"views sharded over {world} GPU(s), volume replicated, no collective"},
+                "e2e": {"value": e2e_value, "unit": "DRRs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "checksum": checksum},
+                "gpu_launches": int(launches), "roofline": roofline, "binding": binding, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the reference arm
+    from deepdrr_b200 import geo, phantoms
+    from deepdrr_b200.scene import SceneTables
+    from oracle import ref_gpu
+
+    B = args.views_per_step
+    carm = phantoms.MobileCArmGeometry()
+    W, H = carm.sensor_width, carm.sensor_height
+    volume = phantoms.thorax_volume(SHAPE, SPACING)
+    st = SceneTables([volume], SPECTRUM)
+    poses = phantoms.c2_poses(1000, seed=1, carm=carm)
+    config = {"workload": WORKLOAD, "views_per_step_per_gpu": B, "sensor": [W, H], "volume": list(SHAPE), "step_mm": STEP_MM}
+    have_gpu_ref = ref_gpu.available()
+    if have_gpu_ref:
+        try:
+            import torch
+
+            have_gpu_ref = torch.cuda.is_available()
+        except Exception:
+            have_gpu_ref = False
+    if have_gpu_ref:
+        ref = ref_gpu.RefProjector([volume.data], st.labels, st.M, [volume.spacing])
+        ref.set_spectrum(st.energies, st.pdf, st.mu)
+        clocks = ClockSampler(0)
+
+        def one_step(s):
+            imgs, pps = [], []
+            for i in range(B):
+                pose = poses[(s * B + i) % 1000]
+                w2i, src, ijk = geo.pose_arrays(pose, [volume])                       # projector.py:802-831
+                inten, pp, ms = ref.project(W, H, STEP_MM, w2i, src, ijk, carm.max_ray_length, threads=8, transpose=True)  # :709-800
+                imgs.append(inten); pps.append(pp)
+                kernel_ms.append(ms)
+            images = np.stack(imgs)                                                   # projector.py:687-688
+            _ = np.stack(pps)
+            # utils.neglog on the host (utils/image_utils.py:18-59), NumPy float32 as in the reference
+            images = images + (images.min(axis=(1, 2), keepdims=True) + np.float32(0.01))
+            images = -np.log(images)
+            lo, hi = images.min(axis=(1, 2), keepdims=True), images.max(axis=(1, 2), keepdims=True)
+            return (images - lo) / (hi - lo)
+
+        kernel_ms = []
+        for s in range(args.warmup):
+            one_step(s)
+        kernel_ms.clear()
+        clocks.start()
+        t0 = time.perf_counter()
+        for s in range(args.warmup, args.warmup + args.steps):
+            out = one_step(s)
+        dt = time.perf_counter() - t0
+        clk = clocks.stop()
+        value = B * args.steps / dt
+        line = {"impl": "reference", "metric": "DRRs/s", "value": value, "unit": "DRRs/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "DRRs/s", "cores": 1, "kind": "reference",
+                                 "sample": f"{B * args.steps} full C2 views; reference CUDA kernel (unmodified, oracle/_ref) on the B200 with the "
+                                           "reference's per-view host flow on one host thread -- the reference has no CPU implementation of this path"},
+                "e2e": {"value": value, "unit": "DRRs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "reference_kernel_ms_per_view": float(np.mean(kernel_ms)), "reference_kernel_only_DRRs_per_s": 1e3 / float(np.mean(kernel_ms)),
+                "clocks": clk, "checksum": float(out[0, H // 2, W // 2])}
+        print(json.dumps(line), flush=True)
+        ref.close()
+        return
+    # no reference cubin (or no GPU): time the CPU oracle port on a bounded sample per step
+    vals = []
+    for s in range(args.warmup + args.steps):
+        c = cpu_baseline_port(volume, st, carm, poses[s % 1000], crop=192)
+        if s >= args.warmup:
+            vals.append(c)
+    value = float(np.mean([c["value"] for c in vals]))
+    line = {"impl": "reference", "metric": "DRRs/s", "value": value, "unit": "DRRs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "cpu_baseline": {"value": value, "unit": "DRRs/s", "cores": vals[0]["cores"], "kind": "port", "sample": vals[0]["sample"]},
+            "e2e": {"value": value, "unit": "DRRs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views-per-step", type=int, default=8)
+    ap.add_argument("--sampler", default="hybrid", choices=["hybrid", "alu", "tex"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

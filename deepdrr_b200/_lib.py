@@ -19,12 +19,13 @@ OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1
 SAMPLER_ALU, SAMPLER_TEX, SAMPLER_HYBRID = 0, 1, 2
 POST_NEGLOG, POST_NOISE, POST_CLIP, POST_COLLECTED = 1, 2, 4, 8
+TUNE_TEX_EIGHTHS, TUNE_KERNEL_VARIANT = 0, 1
 MAX_VOLUMES, MAX_MATERIALS = 8, 16
 
 # every symbol include/drr_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "drr_create", "drr_destroy", "drr_last_error", "drr_set_stream", "drr_set_spectrum", "drr_add_volume",
-    "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_hybrid_share", "drr_set_mesh_buffers",
+    "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_tuning", "drr_set_mesh_buffers",
     "drr_project", "drr_last_timing", "drr_last_sample_count", "drr_launch_count", "drr_synchronize", "drr_version",
 ]
 
@@ -56,7 +57,7 @@ def load() -> ctypes.CDLL:
     lib.drr_clear_volumes.argtypes = [vp]
     lib.drr_set_priorities.argtypes = [vp, vp, vp, ci]
     lib.drr_set_march.argtypes = [vp, cf, ci, ci, ci]
-    lib.drr_set_hybrid_share.argtypes = [vp, ci]
+    lib.drr_set_tuning.argtypes = [vp, ci, ci]
     lib.drr_set_mesh_buffers.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, ci, ci]
     lib.drr_project.argtypes = [vp, ci, ci, ci, vp, vp, vp, cf, cu, cf, cf, cf, ctypes.c_uint64, vp, vp, vp, ci]
     lib.drr_last_timing.argtypes = [vp, vp]

@@ -15,6 +15,7 @@
 // kernels / launchers defined in the other translation units
 cudaError_t drr_launch_march_single(const MarchParams& P, int grid, cudaStream_t s);
 cudaError_t drr_launch_march_general(const MarchParams& P, cudaStream_t s);
+cudaError_t drr_launch_march_warp(const MarchParams& P, int n_sm, cudaStream_t s);
 int drr_march_single_occupancy(int M);
 cudaError_t drr_launch_spectral(const float* area, int n_bins, int M, const float* energies, const float* pdf, const float* mu,
                                 size_t npix, int n_views, float* intensity, float* pprob, int n_sm, cudaStream_t s);
@@ -49,7 +50,7 @@ __global__ void transpose_ik_kernel(const T* __restrict__ in, T* __restrict__ ou
 // One thread per cell base (bi, bj, bk) in [-2, n-2]^3: gathers the 8 clamped corner texels / labels
 // and stores the filter-coefficient record (see hw_trilinear_cell) and the label record.
 __global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t* __restrict__ lab, int ni, int nj, int nk,
-                                   float4* __restrict__ cellc, uint2* __restrict__ celll) {
+                                   float4* __restrict__ cellc, uint2* __restrict__ celll, uint8_t* __restrict__ cellcode) {
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     const int cj = blockIdx.y, ck = blockIdx.z;
     if (ci > ni) return;
@@ -76,6 +77,11 @@ __global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t
         cellc[2 * cell + c] = make_float4(t01 * s, (t10 - t01) * s, (t00 - t01) * s, (t11 - t10) * s);
     }
     celll[cell] = make_uint2(lx, ly);
+    const unsigned l0 = lx & 0xFF;
+    const bool uniform = (lx == ly) && (lx == l0 * 0x01010101u);
+    // clamped cells (base < 0) and the first voxel layer (base == 0) take the integer path, see hw_trilinear_cell
+    const bool interior = bi >= 1 && bj >= 1 && bk >= 1;
+    cellcode[cell] = (uniform && interior) ? (uint8_t)l0 : (uint8_t)0xFF;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -86,6 +92,7 @@ struct VolHost {
     uint8_t* lab = nullptr;
     float4* cellc = nullptr;
     uint2* celll = nullptr;
+    uint8_t* cellcode = nullptr;
     cudaArray_t arr = nullptr;
     cudaTextureObject_t tex = 0;
     int ni = 0, nj = 0, nk = 0;
@@ -107,7 +114,8 @@ struct drr_ctx {
     // march options
     float step = 0.1f;
     int attenuate_outside = 0, air_index = 0, sampler = DRR_SAMPLER_HYBRID;
-    int tex_eighths = 3;
+    int tex_eighths = 5;
+    int variant = 0;  // 0: warp-cooperative march (default), 1: per-ray register-cell march
     // mesh buffers (device pointers, possibly owned)
     int mesh_layers = 0, max_hits = 0, n_mesh_mats = 0;
     const float* hit_alphas = nullptr;
@@ -151,7 +159,7 @@ static int fail(drr_ctx* c, int code, const char* fmt, ...) {
 static void free_volume(VolHost& v) {
     if (v.tex) cudaDestroyTextureObject(v.tex);
     if (v.arr) cudaFreeArray(v.arr);
-    cudaFree(v.dens); cudaFree(v.lab); cudaFree(v.cellc); cudaFree(v.celll);
+    cudaFree(v.dens); cudaFree(v.lab); cudaFree(v.cellc); cudaFree(v.celll); cudaFree(v.cellcode);
     v = VolHost();
 }
 
@@ -286,8 +294,9 @@ int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int 
         const size_t ncell = (size_t)(ni + 1) * (nj + 1) * (nk + 1);
         CUV(cudaMalloc(&v.cellc, ncell * 2 * sizeof(float4)));
         CUV(cudaMalloc(&v.celll, ncell * sizeof(uint2)));
+        CUV(cudaMalloc(&v.cellcode, ncell));
         dim3 cg((ni + 1 + 127) / 128, nj + 1, nk + 1);
-        build_cells_kernel<<<cg, 128, 0, s>>>(v.dens, v.lab, ni, nj, nk, v.cellc, v.celll);
+        build_cells_kernel<<<cg, 128, 0, s>>>(v.dens, v.lab, ni, nj, nk, v.cellc, v.celll, v.cellcode);
         c->launches += 1;
         CUV(cudaGetLastError());
     }
@@ -340,10 +349,11 @@ int drr_set_march(drr_ctx* c, float step, int attenuate_outside, int air_index, 
     return DRR_OK;
 }
 
-int drr_set_hybrid_share(drr_ctx* c, int tex_eighths) {  // tuning knob (not part of the stable ABI)
-    if (!c || tex_eighths < 0 || tex_eighths > 8) return DRR_E_INVALID;
-    c->tex_eighths = tex_eighths;
-    return DRR_OK;
+int drr_set_tuning(drr_ctx* c, int key, int value) {  // tuning knobs (results do not depend on them)
+    if (!c) return DRR_E_INVALID;
+    if (key == DRR_TUNE_TEX_EIGHTHS && value >= 0 && value <= 8) { c->tex_eighths = value; return DRR_OK; }
+    if (key == DRR_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) { c->variant = value; return DRR_OK; }
+    return fail(c, DRR_E_INVALID, "drr_set_tuning: bad key/value %d/%d", key, value);
 }
 
 int drr_set_mesh_buffers(drr_ctx* c, int layers, int max_hits, const float* hit_alphas, const int8_t* hit_facing,
@@ -364,6 +374,8 @@ int drr_set_mesh_buffers(drr_ctx* c, int layers, int max_hits, const float* hit_
     c->additive = additive; c->mesh_mats = mesh_mats;
     return DRR_OK;
 }
+
+static bool h_has_cells(const drr_ctx* c) { return !c->vols.empty() && c->vols[0].cellcode != nullptr; }
 
 static int ensure(drr_ctx* c, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes && *p) return DRR_OK;
@@ -419,7 +431,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     memset(&P, 0, sizeof P);
     for (int v = 0; v < V; v++) {
         const VolHost& h = c->vols[v];
-        P.vol[v].dens = h.dens; P.vol[v].lab = h.lab; P.vol[v].cellc = h.cellc; P.vol[v].celll = h.celll;
+        P.vol[v].dens = h.dens; P.vol[v].lab = h.lab; P.vol[v].cellc = h.cellc; P.vol[v].celll = h.celll; P.vol[v].cellcode = h.cellcode;
         P.vol[v].tex = h.tex; P.vol[v].ni = h.ni; P.vol[v].nj = h.nj; P.vol[v].nk = h.nk;
         P.priority[v] = c->priorities_set ? c->priority[v] : V - 1 - v;  // projector.py:489-492
         P.enabled[v] = c->enabled[v];
@@ -446,10 +458,13 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     if (V == 0) {
         CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
     } else if (single) {
-        int occ = drr_march_single_occupancy(M);
-        if (occ < 1) occ = 1;
-        int grid = c->n_sm * occ;  // persistent: every resident warp pulls 8x4-pixel tiles from the queue
-        CU(c, drr_launch_march_single(P, grid, s));
+        if (c->variant == 0 && h_has_cells(c)) {
+            CU(c, drr_launch_march_warp(P, c->n_sm, s));  // persistent: every warp pulls 8x4-pixel tiles from the queue
+        } else {
+            int occ = drr_march_single_occupancy(M);
+            if (occ < 1) occ = 1;
+            CU(c, drr_launch_march_single(P, c->n_sm * occ, s));
+        }
         c->launches += 1;
     } else {
         if (V > 4 || M > 8) return fail(c, DRR_E_INVALID, "drr_project: the general kernel supports up to 4 volumes / 8 materials");

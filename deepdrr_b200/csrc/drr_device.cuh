@@ -20,6 +20,7 @@ struct VolDev {
     const uint8_t* lab;   // [nk][nj][ni] labels (global material index)
     const float4* cellc;  // [(nk+1)][(nj+1)][(ni+1)][2] per-cell filter coefficients (ALU sampler)
     const uint2* celll;   // [(nk+1)][(nj+1)][(ni+1)]    per-cell 8 corner labels
+    const uint8_t* cellcode;  // same shape: the label if all 8 corners agree and the cell is interior, else 0xFF
     cudaTextureObject_t tex;
     int ni, nj, nk;
     int pad;
@@ -195,6 +196,31 @@ __device__ __forceinline__ float hw_trilinear_cell(float xr, float yr, float zr,
     acc = __fmaf_rn(Y00, c1.z, acc);
     acc = __fmaf_rn(Y11, c1.w, acc);
     return acc;
+}
+
+// Same arithmetic with the two z-slices packed into f32x2 lanes (FFMA2 / FADD2 / FMUL2, sm_100+): the
+// kernel is issue-bound, so halving the instruction count of the slice-symmetric part pays even though
+// the FMA pipe does the same work.  Record layout for this form (built when a cell is staged into
+// shared memory): A = (c0.x, c1.x, c0.y, c1.y), B = (c0.z, c1.z, c0.w, c1.w).
+__device__ __forceinline__ float hw_trilinear_cell2(float xr, float yr, float zr, const float4& A, const float4& B) {
+    const float C = DRR_MAGIC;
+    const float af = __fsub_rn(__fadd_rn(__fmaf_rn(xr, 256.0f, 0x1p-15f), C), C);
+    const float bf = __fsub_rn(__fadd_rn(__fmaf_rn(yr, 256.0f, 0x1p-15f), C), C);
+    const float cf = __fsub_rn(__fadd_rn(__fmaf_rn(zr, 256.0f, 0x1p-15f), C), C);
+    const float bp = __fmaf_rn(bf, 0x1p-8f, af == 256.0f ? -0x1p-17f : 0x1p-17f);
+    const float bq = __fmaf_rn(bf, -0x1p-8f, 1.0f + 0x1p-17f);
+    const float2 cc = make_float2(cf, cf), CC = make_float2(C, C), nCC = make_float2(-C, -C);
+    const float2 wz = __ffma2_rn(cc, make_float2(-1.0f, 1.0f), make_float2(256.0f, 0.0f));                        // (256 - c, c)
+    const float2 wp = __ffma2_rn(cc, make_float2(-0x1p-8f, 0x1p-8f), make_float2(1.0f + 0x1p-17f, 0x1p-17f));      // wz/256 + 2^-17
+    const float2 X1 = __fadd2_rn(__ffma2_rn(wp, make_float2(af, af), CC), nCC);
+    const float2 X0 = __ffma2_rn(X1, make_float2(-1.0f, -1.0f), wz);
+    const float2 Y11 = __fadd2_rn(__ffma2_rn(X1, make_float2(bp, bp), CC), nCC);
+    const float2 Y00 = __fadd2_rn(__ffma2_rn(X0, make_float2(bq, bq), CC), nCC);
+    float2 r = __fmul2_rn(wz, make_float2(A.x, A.y));
+    r = __ffma2_rn(X1, make_float2(A.z, A.w), r);
+    r = __ffma2_rn(Y00, make_float2(B.x, B.y), r);
+    r = __ffma2_rn(Y11, make_float2(B.z, B.w), r);
+    return __fadd_rn(r.x, r.y);
 }
 
 // Trilinear one-hot material weights of the reference (K.cu:434-455), full fp32 weights.

@@ -1,0 +1,302 @@
+// Warp-cooperative single-volume ray march (the hot path of BASELINE C1/C2), libdrr_b200, sm_100a.
+//
+// Replaces the march of the reference's `projectKernel` (project_kernel.cu:334-553, "K.cu:n") for
+// NUM_VOLUMES == 1 without meshes / outside air.  Same arithmetic as the per-ray kernel in
+// drr_march.cu; different execution shape, chosen from its ncu profile (profiles/r01_*):
+// per-lane "cell changed" reloads fired on 62 % of warp steps with 8 of 32 lanes active and cost more
+// issue slots than the interpolation itself.
+//
+// Here a warp owns an 8x4 pixel tile and walks its 32 rays in lock step over the global step index
+// t (all rays start at minAlpha ~ ray_length, so equal t means a coherent sample front).  For every
+// segment of <= SEG steps the warp
+//   1. bounds the voxel cells its rays will touch (two FMAs per lane + redux.sync min/max),
+//   2. stages those cells once, cooperatively, into shared memory: the 32 B filter-coefficient
+//      record (ALU role only) and the 1 B label code of each cell (coalesced 128-bit loads),
+//   3. marches the segment out of shared memory with no divergence: one LDS.U8 (+ two LDS.128) per
+//      sample, the texture-unit arithmetic on the FMA pipes (ALU role) or one tex3D (TEX role).
+// Warps of both roles share every SM, so the TEX pipe and the FMA pipes are busy together.
+#include <math_constants.h>
+
+#include "drr_device.cuh"
+
+#define TILE_W 8
+#define TILE_H 4
+#define SEG 32
+#define MAXC 256                       // cells staged per warp and segment
+#define WARP_SMEM (MAXC * 32 + MAXC)   // coefficient records + codes
+#define WARPS_PER_BLOCK 8
+
+// ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
+template <int NM>
+__device__ __forceinline__ void w_checkin(float cur, int& live, float* acc) {
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc[m] = (live == m) ? cur : acc[m];
+    live = -1;
+}
+template <int NM>
+__device__ __forceinline__ float w_checkout(int label, int& live, const float* acc) {
+    float cur = 0.0f;
+#pragma unroll
+    for (int m = 0; m < NM; m++) cur = (label == m) ? acc[m] : cur;
+    live = label;
+    return cur;
+}
+
+// Generic sample straight from global memory: mixed-label / clamped cells and half-weighted ends.
+template <int NM, bool USE_TEX>
+__device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float y, float z, float weight, float* acc) {
+    float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
+    float bx = floorf(px), by = floorf(py), bz = floorf(pz);
+    int ci = min(max((int)bx + 2, 0), vol.ni), cj = min(max((int)by + 2, 0), vol.nj), ck = min(max((int)bz + 2, 0), vol.nk);
+    uint2 lab8 = __ldg(vol.celll + ((size_t)ck * (vol.nj + 1) + cj) * (vol.ni + 1) + ci);
+    float seg[NM];
+#pragma unroll
+    for (int m = 0; m < NM; m++) seg[m] = 0.0f;
+    seg_weights<NM>(__fsub_rn(px, bx), __fsub_rn(py, by), __fsub_rn(pz, bz), lab8, seg);
+    float cx = __fadd_rn(px, 0.5f), cy = __fadd_rn(py, 0.5f), cz = __fadd_rn(pz, 0.5f);  // K.cu:542
+    float rho = USE_TEX ? tex3D<float>(vol.tex, cx, cy, cz) : hw_trilinear_raw(vol, cx, cy, cz);
+    float wr = __fmul_rn(weight, rho);
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc[m] = __fmaf_rn(wr, seg[m], acc[m]);
+}
+
+template <int NM, bool USE_TEX>
+__device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
+                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps) {
+    const VolDev& vol = P.vol[0];
+    const float step = P.step;
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc[m] = 0.0f;
+
+    // ---- per-lane ray set-up (K.cu:220-334) ----------------------------------------------------
+    float dx = 0.f, dy = 0.f, dz = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f;
+    const float sx = vw.src[0][0], sy = vw.src[0][1], sz = vw.src[0][2];
+    int num_steps = 0;
+    if (pixel_ok && P.enabled[0] != 0) {
+        Ray r = make_ray(vw.w2i, udx, vdx);
+        ray_dir_ijk(r, vw.ijk[0], dx, dy, dz);
+        if (slab_test(dx, dy, dz, sx, sy, sz, vol.ni, vol.nj, vol.nk, P.max_ray_length, lo, hi)) {
+            float minAlpha = fminf(r.ray_length, lo), maxAlpha = fmaxf(0.0f, hi);         // K.cu:242-244, 321-322
+            num_steps = (int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), step));        // K.cu:334
+            num_steps = max(num_steps, 0);
+            alpha = minAlpha;
+        }
+    }
+    my_steps += (unsigned)num_steps;
+    const int last = num_steps - 1;
+    const int t_end = __reduce_max_sync(0xffffffffu, num_steps);
+    if (t_end == 0) return;
+
+    // ---- before the volume: replay the fp32 alpha accumulation only (K.cu:552) ----
+    // Lower bound of the first in-range step of each lane; `drift` bounds how far the accumulated
+    // alpha can be from minAlpha + t*step.
+    int t = 0;
+    {
+        int n0 = 0x7fffffff;
+        if (num_steps > 0) {
+            float drift = (float)num_steps * 0x1p-24f * fmaxf(hi, 1.0f);
+            n0 = max(0, (int)floorf(__fdiv_rn(__fsub_rn(__fsub_rn(lo, alpha), drift), step)) - 2);
+            n0 = min(n0, num_steps);
+        }
+        const int n_skip = __reduce_min_sync(0xffffffffu, n0);
+        for (; t < n_skip; t++) alpha = __fadd_rn(alpha, step);
+    }
+
+    float cur = 0.0f;
+    int live = -1;
+    const int nxm = vol.ni - 2, nym = vol.nj - 2, nzm = vol.nk - 2;  // max cell base
+
+    while (t < t_end) {
+        // ---- 1. bound the cells of this segment ------------------------------------------------
+        int S = min(SEG, t_end - t);
+        int blx, bly, blz, nx, ny, nz;
+        bool any;
+        for (;;) {
+            float a1 = __fmaf_rn((float)S, step, alpha);
+            bool part = (t < num_steps) && !(a1 < lo - 0.01f) && !(alpha > hi + 0.01f);
+            float p0x = __fmaf_rn(alpha, dx, sx) - 1.0f, p1x = __fmaf_rn(a1, dx, sx) - 1.0f;
+            float p0y = __fmaf_rn(alpha, dy, sy) - 1.0f, p1y = __fmaf_rn(a1, dy, sy) - 1.0f;
+            float p0z = __fmaf_rn(alpha, dz, sz) - 1.0f, p1z = __fmaf_rn(a1, dz, sz) - 1.0f;
+            int lx = max(-2, min(nxm, (int)floorf(fminf(p0x, p1x) - 0.01f))), hx = max(-2, min(nxm, (int)floorf(fmaxf(p0x, p1x) + 0.01f)));
+            int ly = max(-2, min(nym, (int)floorf(fminf(p0y, p1y) - 0.01f))), hy = max(-2, min(nym, (int)floorf(fmaxf(p0y, p1y) + 0.01f)));
+            int lz = max(-2, min(nzm, (int)floorf(fminf(p0z, p1z) - 0.01f))), hz = max(-2, min(nzm, (int)floorf(fmaxf(p0z, p1z) + 0.01f)));
+            if (!part) { lx = ly = lz = 0x7fffffff; hx = hy = hz = (int)0x80000000; }
+            blx = __reduce_min_sync(0xffffffffu, lx); bly = __reduce_min_sync(0xffffffffu, ly); blz = __reduce_min_sync(0xffffffffu, lz);
+            int bhx = __reduce_max_sync(0xffffffffu, hx), bhy = __reduce_max_sync(0xffffffffu, hy), bhz = __reduce_max_sync(0xffffffffu, hz);
+            any = bhx >= blx;
+            if (!any) break;
+            nx = bhx - blx + 1; ny = bhy - bly + 1; nz = bhz - blz + 1;
+            if (nx * ny * nz <= MAXC || S == 1) break;
+            S >>= 1;
+        }
+        if (!any) {  // nobody samples in this segment: just advance alpha
+            for (int s = 0; s < S; s++) alpha = __fadd_rn(alpha, step);
+            t += S;
+            continue;
+        }
+        const int ncell = min(nx * ny * nz, MAXC);  // S == 1 always fits (<= 27 cells); min() is a guard only
+
+        // ---- 2. stage the cells ----------------------------------------------------------------
+        __syncwarp();
+        int first_code = -1;
+        bool same = true;
+        {
+            const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
+            for (int e = lane; e < ncell; e += 32) {
+                int row = (int)(((float)e + 0.5f) * inv_nx);  // e / nx (exact for e < 2^16)
+                int cx = e - row * nx;
+                int cz = (int)(((float)row + 0.5f) * inv_ny);
+                int cy = row - cz * ny;
+                size_t cell = ((size_t)(blz + cz + 2) * (vol.nj + 1) + (bly + cy + 2)) * (vol.ni + 1) + (blx + cx + 2);
+                const int cc = __ldg(vol.cellcode + cell);
+                s_code[e] = (uint8_t)cc;
+                same = same && (first_code < 0 || cc == first_code);
+                first_code = cc;
+                if (!USE_TEX) {  // slices interleaved for the packed f32x2 form (hw_trilinear_cell2)
+                    const float4 c0 = __ldg(vol.cellc + 2 * cell), c1 = __ldg(vol.cellc + 2 * cell + 1);
+                    s_coef[2 * e] = make_float4(c0.x, c1.x, c0.y, c1.y);
+                    s_coef[2 * e + 1] = make_float4(c0.z, c1.z, c0.w, c1.w);
+                }
+            }
+        }
+        __syncwarp();
+        // one label for the whole box?  (lanes without a cell inherit lane 0's code)
+        const int code0 = __shfl_sync(0xffffffffu, first_code, 0);
+        if (first_code < 0) first_code = code0;
+        const bool seg_uniform = __all_sync(0xffffffffu, same && first_code == code0) && code0 != 0xFF;
+        // every lane inside its [lo, hi] window and away from its half-weighted end samples for the whole segment?
+        const bool lane_allin = (t > 0) && (t + S < num_steps) && !(alpha < lo) &&
+                                !(__fmaf_rn((float)S, step, alpha) + 0.01f > hi);
+        const bool seg_allin = __all_sync(0xffffffffu, lane_allin);
+
+        const float b1x = (float)(blx + 1), b1y = (float)(bly + 1), b1z = (float)(blz + 1);
+        const float fnx = (float)nx, fny = (float)ny;
+        if (seg_uniform && seg_allin) {
+            // ---- 3a. fast segment: one label, no range checks ------------------------------------
+            if (live != code0) {
+                w_checkin<NM>(cur, live, acc);
+                cur = w_checkout<NM>(code0, live, acc);
+            }
+            const int t_stop = t + S;
+            if (USE_TEX) {
+#pragma unroll 4
+                for (; t < t_stop; t++) {
+                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
+                    cur = __fadd_rn(cur, tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f)));  // K.cu:542
+                    alpha = __fadd_rn(alpha, step);  // K.cu:552
+                }
+            } else {
+#pragma unroll 2
+                for (; t < t_stop; t++) {
+                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
+                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                    const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
+                    const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                    cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                    alpha = __fadd_rn(alpha, step);  // K.cu:552
+                }
+            }
+            continue;
+        }
+
+        // ---- 3b. general segment: per-sample label code and range check ----------------------------
+        for (int s = 0; s < S; s++, t++) {
+            const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
+            const bool inr = (t < num_steps) && !(alpha < lo) && !(alpha > hi);  // K.cu:472
+            float rho = 0.0f;
+            if (USE_TEX && inr) rho = tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
+            // cell-local coordinates: l = p - box_lo, p = x - 1 (K.cu:402-404); exact for x >= 1
+            const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+            const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+            int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
+            idx = inr ? min(max(idx, 0), ncell - 1) : 0;
+            int code = s_code[idx];
+            if ((t == 0) | (t == last)) code = 0xFF;  // half-weighted end samples take the generic path
+            if (inr) {
+                if (code != live) {
+                    w_checkin<NM>(cur, live, acc);
+                    if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
+                }
+                if (code != 0xFF) {
+                    if (USE_TEX) {
+                        cur = __fadd_rn(cur, rho);
+                    } else {
+                        const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                        cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                    }
+                } else {
+                    w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                }
+            }
+            alpha = __fadd_rn(alpha, step);  // K.cu:552
+        }
+    }
+    w_checkin<NM>(cur, live, acc);
+}
+
+template <int NM>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) march_warp_kernel(const __grid_constant__ MarchParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
+    uint8_t* s_code = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
+    const int warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const bool tex_role = ((warp_global * 5) & 7) < P.tex_eighths;  // spread roles over the warp slots of an SM
+    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+    const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
+    const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
+    const size_t npix = (size_t)P.W * P.H;
+    const float step = P.step;
+    unsigned long long my_steps = 0;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const unsigned view = tile / tiles_per_view;
+        const unsigned tv = tile - view * tiles_per_view;
+        const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
+        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
+        const bool ok = udx < P.W && vdx < P.H;
+        float acc[NM];
+        const ViewDev& vw = P.views[view];
+        if (tex_role) march_tile<NM, true>(P, vw, udx, vdx, ok, s_coef, s_code, lane, acc, my_steps);
+        else march_tile<NM, false>(P, vw, udx, vdx, ok, s_coef, s_code, lane, acc, my_steps);
+        if (ok) {
+            float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
+#pragma unroll
+            for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[m], step), 10.0f);  // K.cu:565-567, 582-584
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd(P.sample_count, my_steps);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NM>
+static cudaError_t launch_warp_nm(const MarchParams& P, int n_sm, cudaStream_t s) {
+    const size_t smem = (size_t)WARP_SMEM * WARPS_PER_BLOCK;
+    cudaError_t e = cudaFuncSetAttribute(march_warp_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_warp_kernel<NM>, 32 * WARPS_PER_BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    march_warp_kernel<NM><<<n_sm * occ, 32 * WARPS_PER_BLOCK, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_march_warp(const MarchParams& P, int n_sm, cudaStream_t s) {
+    switch (P.M) {
+        case 1: return launch_warp_nm<1>(P, n_sm, s);
+        case 2: return launch_warp_nm<2>(P, n_sm, s);
+        case 3: return launch_warp_nm<3>(P, n_sm, s);
+        case 4: return launch_warp_nm<4>(P, n_sm, s);
+        case 5: return launch_warp_nm<5>(P, n_sm, s);
+        case 6: return launch_warp_nm<6>(P, n_sm, s);
+        case 7: return launch_warp_nm<7>(P, n_sm, s);
+        case 8: return launch_warp_nm<8>(P, n_sm, s);
+        default: return cudaErrorInvalidValue;
+    }
+}

@@ -290,6 +290,24 @@ class Projector(object):
             self.max_ray_length = float(max_ray_length)
         return self._project_batch(camera_projections, want="area")
 
+    def project_arrays(self, world_from_index, source_ijk, ijk_from_world, sensor_size, max_ray_length: float,
+                       want: str = "intensity", raw: bool = False, out=None):
+        """Extra, lower-level entry point: project from the kernel-level per-view arrays.
+
+        ``world_from_index`` [n, 9], ``source_ijk`` [n, V, 3], ``ijk_from_world`` [n, V, 12] are exactly the
+        arrays ``_update_object_locations`` uploads in the reference (projector.py:802-831), so identical
+        inputs can be fed to this projector, the reference kernel and the CPU oracle.
+        ``want``: "intensity" -> [n, H, W] (post-processed like ``project`` unless ``raw``), "area" -> [n, M, H, W].
+        """
+        if not self.initialized:
+            raise RuntimeError("Projector has not been initialized.")
+        w2i = np.ascontiguousarray(world_from_index, dtype=np.float32).reshape(-1, 9)
+        n, V = w2i.shape[0], len(self.volumes)
+        src = np.ascontiguousarray(source_ijk, dtype=np.float32).reshape(n, max(V, 1), 3)
+        ijk = np.ascontiguousarray(ijk_from_world, dtype=np.float32).reshape(n, max(V, 1), 12)
+        self.max_ray_length = float(max_ray_length)
+        return self._run(w2i, src, ijk, int(sensor_size[0]), int(sensor_size[1]), want, out, raw, None)
+
     def _pose_arrays(self, camera_projections):
         n, V = len(camera_projections), len(self.volumes)
         w2i = np.zeros((n, 9), dtype=np.float32)
@@ -303,14 +321,17 @@ class Projector(object):
         return w2i, src, ijk
 
     def _project_batch(self, camera_projections, want="intensity", out=None, raw=False):
-        lib, h = _lib.load(), self._h
-        n = len(camera_projections)
         sizes = {tuple(p.intrinsic.sensor_size) for p in camera_projections}
         if len(sizes) != 1:
             raise ValueError("all camera projections of one call must share the sensor size")
         W, H = sizes.pop()
-        self.output_shape = (W, H)
         w2i, src, ijk = self._pose_arrays(camera_projections)
+        return self._run(w2i, src, ijk, W, H, want, out, raw, camera_projections[0].intrinsic)
+
+    def _run(self, w2i, src, ijk, W, H, want, out, raw, intrinsic):
+        lib, h = _lib.load(), self._h
+        n = w2i.shape[0]
+        self.output_shape = (W, H)
         V = len(self.volumes)
         pr = np.ascontiguousarray(self.priorities, dtype=np.int32)
         en = np.ascontiguousarray([1 if getattr(v, "enabled", True) else 0 for v in self.volumes], dtype=np.int32)
@@ -328,7 +349,9 @@ class Projector(object):
                 flags |= _lib.POST_NEGLOG
         pixel_area = 1.0
         if flags & _lib.POST_COLLECTED:
-            k = camera_projections[0].intrinsic
+            k = intrinsic
+            if k is None:
+                raise ValueError("collected_energy needs camera intrinsics (use project(), not project_arrays())")
             pixel_area = (self.source_to_detector_distance / k.fx) * (self.source_to_detector_distance / k.fy)
         seed = (self.noise_seed if self.noise_seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFF) + self._noise_calls
         self._noise_calls += 1
@@ -362,8 +385,15 @@ class Projector(object):
         _lib.check(_lib.load().drr_launch_count(self._h, ctypes.byref(s)), self._h)
         return int(s.value)
 
+    def set_stream(self, cuda_stream_ptr: int):
+        """Run this projector's GPU work on a caller-owned cudaStream_t (0 / None = its own stream)."""
+        _lib.check(_lib.load().drr_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)), self._h)
+
     def set_hybrid_share(self, tex_eighths: int):
-        _lib.check(_lib.load().drr_set_hybrid_share(self._h, int(tex_eighths)), self._h)
+        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_TEX_EIGHTHS, int(tex_eighths)), self._h)
+
+    def set_kernel_variant(self, variant: int):
+        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_KERNEL_VARIANT, int(variant)), self._h)
 
     def project_over_carm_range(self, *a, **k):
         raise DeprecationError("project_over_carm_range is deprecated. See README for alternatives.")

@@ -84,9 +84,14 @@ int drr_set_priorities(drr_ctx* ctx, const int* priority, const int* enabled, in
  * (projector.py:554-568, -D ATTENUATE_OUTSIDE_VOLUME / AIR_INDEX), sampler = DRR_SAMPLER_*. */
 int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int air_index, int sampler);
 
-/* Tuning knob of DRR_SAMPLER_HYBRID: how many of every 8 warps fetch density through the texture
- * unit (the rest emulate it on the FMA pipes).  0..8, default 3. */
-int drr_set_hybrid_share(drr_ctx* ctx, int tex_eighths);
+/* Tuning knobs; results do not depend on them.
+ *   DRR_TUNE_TEX_EIGHTHS    DRR_SAMPLER_HYBRID: how many of every 8 warps fetch density through the
+ *                           texture unit (the rest emulate it on the FMA pipes), 0..8.
+ *   DRR_TUNE_KERNEL_VARIANT single-volume march: 0 = warp-cooperative shared-memory staging (default),
+ *                           1 = per-ray register cell cache. */
+#define DRR_TUNE_TEX_EIGHTHS 0
+#define DRR_TUNE_KERNEL_VARIANT 1
+int drr_set_tuning(drr_ctx* ctx, int key, int value);
 
 /* Mesh inputs of projectKernel (project_kernel.cu:172-177, 363-375, 498-517, 569-579), per view,
  * device or host pointers; NULL disables.  Produced by drr_mesh_* (ray-triangle) or by the caller.

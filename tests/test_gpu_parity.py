@@ -1,0 +1,280 @@
+"""Parity tests proper: the CUDA path (through Projector -> ctypes -> libdrr_b200.so) against
+  (a) golden outputs of the reference's own CUDA kernel (tests/golden, reference run on a B200),
+  (b) the CPU oracle on fresh poses,
+  (c) the reference kernel itself, live, when oracle/_ref was shipped with the repo snapshot,
+plus size-independent properties at BASELINE.json's full sizes and the reference's edge cases.
+
+Tolerances (north_star): per-material line integrals 1e-5 relative per pixel, intensity 1e-4 relative;
+labels / indexing are exercised through exact-zero and bit-equality checks.
+"""
+import numpy as np
+import pytest
+
+import cases
+from deepdrr_b200 import Projector, geo, phantoms
+from oracle import cpu_oracle
+
+pytestmark = pytest.mark.gpu
+
+LINE_RTOL = 1e-5
+INT_RTOL = 1e-4
+
+
+def _projector(volumes, spectrum, priorities, sampler, W, H, **kw):
+    k = geo.CameraIntrinsicTransform.from_sizes((W, H), 1.0, 1000.0)
+    return Projector(volumes, priorities=priorities, spectrum=spectrum, step=kw.pop("step", 0.1), neglog=kw.pop("neglog", False),
+                     camera_intrinsics=k, sampler=sampler, **kw)
+
+
+def _compare_with_golden(name, samplers, views=None):
+    volumes, spectrum, priorities = cases.scene(name)
+    g = cases.golden(name)
+    W, H, sub = int(g["W"]), int(g["H"]), int(g["sub"])
+    nv = cases.n_views(g)
+    ids = [i for i in range(nv) if views is None or i in views]
+    w2i = np.stack([g[f"w2i_{i}"] for i in ids])
+    src = np.stack([g[f"src_{i}"] for i in ids])
+    ijk = np.stack([g[f"ijk_{i}"] for i in ids])
+    for sampler in samplers:
+        with _projector(volumes, spectrum, priorities, sampler, W, H, step=float(g["step"])) as p:
+            area = p.project_arrays(w2i, src, ijk, (W, H), float(g["max_ray_length"]), want="area")
+            inten = p.project_arrays(w2i, src, ijk, (W, H), float(g["max_ray_length"]), want="intensity", raw=True)
+            assert p.launch_count() > 0
+        for n, i in enumerate(ids):
+            gl, gi = g[f"lineint_{i}"], g[f"intensity_{i}"]
+            a, im = area[n][:, ::sub, ::sub], inten[n][::sub, ::sub]
+            for m in range(a.shape[0]):
+                mask = gl[m] > 0
+                assert np.all(a[m][~mask] == 0), f"{name}/{sampler}: material {m} leaked into pixels where the reference has none"
+                if mask.any():
+                    err = cases.rel_err(a[m], gl[m])[mask].max()
+                    assert err <= LINE_RTOL, f"{name}/{sampler} view {i} material {m}: line integral rel err {err:.2e}"
+            err = cases.rel_err(im, gi).max()
+            assert err <= INT_RTOL, f"{name}/{sampler} view {i}: intensity rel err {err:.2e}"
+
+
+@pytest.mark.parametrize("name", ["c1", "thorax_small"])
+def test_single_volume_vs_reference_kernel_goldens(name):
+    _compare_with_golden(name, ("alu", "tex", "hybrid"))
+
+
+@pytest.mark.parametrize("name", ["multivol3", "multivol2_sameprio"])
+def test_multi_volume_vs_reference_kernel_goldens(name):
+    # priorities, same-priority averaging and the shared label cache quirk
+    _compare_with_golden(name, ("alu",))
+
+
+def test_full_size_c2_vs_reference_kernel_golden():
+    """BASELINE config 2: 512x512x400 CT -> 1536^2 detector, view 0, every 8th pixel stored."""
+    _compare_with_golden("c2", ("hybrid", "alu"), views=[0])
+
+
+def test_per_ray_kernel_variant_matches_too():
+    volumes, spectrum, priorities = cases.scene("c1")
+    g = cases.golden("c1")
+    W, H, sub = int(g["W"]), int(g["H"]), int(g["sub"])
+    with _projector(volumes, spectrum, priorities, "hybrid", W, H) as p:
+        p.set_kernel_variant(1)
+        area = p.project_arrays(g["w2i_0"][None], g["src_0"][None], g["ijk_0"][None], (W, H), float(g["max_ray_length"]), want="area")[0]
+    for m in range(area.shape[0]):
+        mask = g["lineint_0"][m] > 0
+        assert cases.rel_err(area[m][::sub, ::sub], g["lineint_0"][m])[mask].max() <= LINE_RTOL
+
+
+def test_fresh_poses_vs_cpu_oracle_including_odd_sensor_sizes():
+    """Poses that are not in any golden file; sensor sizes that are not multiples of the 8x4 warp tile."""
+    vol_ = phantoms.thorax_volume((64, 64, 50), (6.4, 6.4, 8.0), seed=7)
+    st = cases.tables([vol_], "60KV_AL35", None)
+    for (W, H), seed in (((37, 23), 11), ((64, 48), 12), ((1, 1), 13)):
+        carm = phantoms.MobileCArmGeometry(sensor_width=W, sensor_height=H, pixel_size=298.0 / max(W, H))
+        poses = phantoms.c2_poses(2, seed=seed, carm=carm)
+        with Projector(vol_, spectrum="60KV_AL35", step=0.25, neglog=False, camera_intrinsics=carm.camera_intrinsics, sampler="hybrid") as p:
+            area = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+            img = p.project(*poses, max_ray_length=carm.max_ray_length)
+        for n, pose in enumerate(poses):
+            w2i, src, ijk = geo.pose_arrays(pose, [vol_])
+            r = cpu_oracle.project([vol_.data], st.labels, st.M, W, H, 0.25, w2i, src, ijk, carm.max_ray_length, st.energies, st.pdf, st.mu)
+            for m in range(st.M):
+                mask = r.area[m] > 0
+                if mask.any():
+                    assert cases.rel_err(area[n, m], r.area[m])[mask].max() <= LINE_RTOL
+                assert np.all(area[n, m][~mask] == 0)
+            assert cases.rel_err(img[n], r.intensity).max() <= INT_RTOL
+
+
+def test_live_reference_kernel_on_new_poses():
+    """Runs the reference's own cubin (oracle/_ref, built from /root/reference by oracle/Makefile) next to
+    the CUDA path on poses generated here."""
+    from oracle import ref_gpu
+
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not shipped")
+    volumes, spectrum, priorities = cases.scene("thorax_small")
+    st = cases.tables(volumes, spectrum, priorities)
+    carm = phantoms.MobileCArmGeometry(sensor_width=200, sensor_height=160, pixel_size=1.49)
+    poses = phantoms.c2_poses(3, seed=99, carm=carm)
+    ref = ref_gpu.RefProjector([v.data for v in volumes], st.labels, st.M, lineint=True)
+    refp = ref_gpu.RefProjector([v.data for v in volumes], st.labels, st.M)
+    refp.set_spectrum(st.energies, st.pdf, st.mu)
+    with Projector(volumes, spectrum=spectrum, neglog=False, camera_intrinsics=carm.camera_intrinsics, sampler="hybrid") as p:
+        area = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+        img = p.project(*poses, max_ray_length=carm.max_ray_length)
+    for n, pose in enumerate(poses):
+        w2i, src, ijk = geo.pose_arrays(pose, volumes)
+        li = ref.line_integrals(200, 160, 0.1, w2i, src, ijk, carm.max_ray_length)
+        ri, _, _ = refp.project(200, 160, 0.1, w2i, src, ijk, carm.max_ray_length)
+        for m in range(st.M):
+            mask = li[m] > 0
+            assert cases.rel_err(area[n, m], li[m])[mask].max() <= LINE_RTOL
+        assert cases.rel_err(img[n], ri).max() <= INT_RTOL
+    ref.close(); refp.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# properties and edge cases
+# ---------------------------------------------------------------------------------------------
+def test_density_scaling_is_exactly_linear_and_batch_equals_single():
+    v = phantoms.thorax_volume((48, 48, 40), (8.5, 8.5, 10.0), seed=2)
+    carm = phantoms.MobileCArmGeometry(sensor_width=96, sensor_height=64, pixel_size=3.0)
+    poses = phantoms.c2_poses(3, seed=5, carm=carm)
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=carm.camera_intrinsics) as p:
+        a1 = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+        singles = np.stack([p.project_line_integrals(q, max_ray_length=carm.max_ray_length)[0] for q in poses])
+    assert np.array_equal(a1, singles)                       # a batch is exactly the per-view results
+    v2 = phantoms.thorax_volume((48, 48, 40), (8.5, 8.5, 10.0), seed=2)
+    v2.data *= 2.0                                            # power of two: every product stays exact
+    with Projector(v2, spectrum="90KV_AL40", neglog=False, camera_intrinsics=carm.camera_intrinsics) as p:
+        a2 = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+    assert np.array_equal(a2, 2.0 * a1)
+
+
+def test_homogeneous_box_line_integral_is_rho_times_chord():
+    """Analytic KAT: constant density -> line integral = rho * step * (#in-range samples - 1/2 per
+    half-weighted end); here checked against rho * chord length to within one step."""
+    n = 40
+    hu = np.full((n, n, n), 40.0, dtype=np.float32)
+    from deepdrr_b200 import Volume
+
+    c = (n - 1) / 2.0
+    v = Volume.from_hu(hu, anatomical_from_IJK=geo.FrameTransform(np.array([[1, 0, 0, -c], [0, 1, 0, -c], [0, 0, 1, -c], [0, 0, 0, 1.0]])))
+    rho = float(v.data[0, 0, 0])
+    proj, mrl = phantoms.c1_camera(16, direction=(0.0, 1.0, 0.0))
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=proj.intrinsic) as p:
+        a = p.project_line_integrals(proj, max_ray_length=mrl)[0]
+    mats = p.all_materials
+    soft = a[mats.index("soft tissue")]
+    # central ray: chord = n voxels = 40 mm -> rho * 4.0 g/cm^2, edge effects below one step (0.1 mm)
+    assert abs(soft[8, 8] - rho * n / 10.0) <= rho * 0.011
+    assert np.all(a[mats.index("bone")] == 0) and np.all(a[mats.index("air")] == 0)
+
+
+def test_disabled_volume_and_missed_volume_give_unattenuated_beam():
+    v = phantoms.c1_volume(32)
+    proj, mrl = phantoms.c1_camera(24)
+    st = cases.tables([v], "90KV_AL40", None)
+    i0 = np.float32(0)
+    pp0 = np.float32(0)
+    for b in range(st.n_bins):  # project_kernel.cu:637-646 with zero area densities
+        pp0 = np.float32(pp0 + st.pdf[b])
+        i0 = np.float32(np.float32(st.energies[b]) * st.pdf[b] + i0)
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=proj.intrinsic) as p:
+        v.enabled = False
+        img = p.project(proj, max_ray_length=mrl)
+        v.enabled = True
+        away, _ = phantoms.c1_camera(24, direction=(0.0, 1.0, 0.0))
+        away = phantoms.look_at_projection((0, 2000.0, 0), (0, 1.0, 0), (0, 0, 1), proj.intrinsic)  # looking away from the volume
+        img2 = p.project(away, max_ray_length=mrl)
+        p.neglog = True
+        z = p.project(away, max_ray_length=mrl)
+    assert np.allclose(img, i0, rtol=2e-6) and np.allclose(img2, i0, rtol=2e-6)
+    assert np.all(z == 0)  # constant image -> neglog maps it to 0 (utils/image_utils.py:42-49)
+
+
+def test_neglog_clip_and_batch_semantics_match_host_restatement():
+    volumes, spectrum, priorities = cases.scene("c1")
+    proj, mrl = phantoms.c1_camera(64)
+    proj2, _ = phantoms.c1_camera(64, direction=(1.0, 0.2, 0.0))
+    with Projector(volumes, spectrum=spectrum, neglog=False, camera_intrinsics=proj.intrinsic) as p:
+        raw = p.project(proj, proj2, max_ray_length=mrl)
+        p.neglog = True
+        nl = p.project(proj, proj2, max_ray_length=mrl)
+        p.intensity_upper_bound = float(np.median(raw))
+        nlc = p.project(proj, proj2, max_ray_length=mrl)
+    assert raw.shape == (2, 64, 64) and raw.dtype == np.float32
+    assert np.allclose(nl, cpu_oracle.neglog(raw), atol=3e-6, rtol=0)
+    assert nl.min() == 0.0 and nl.max() == 1.0
+    assert np.allclose(nlc, cpu_oracle.neglog(np.minimum(raw, np.float32(np.median(raw)))), atol=3e-6, rtol=0)
+
+
+def test_poisson_noise_statistics():
+    """add_noise (analytic_generators.py:10-18) is unseeded NumPy in the reference -> statistical parity only:
+    zero-mean, variance = sum(k^2) * I^2 / (photon_prob * photon_count) within 5 %."""
+    v = phantoms.c1_volume(32)
+    proj, mrl = phantoms.c1_camera(128)
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=proj.intrinsic, add_noise=True, photon_count=2000,
+                   noise_seed=1234) as p:
+        noisy = np.stack([p.project(proj, max_ray_length=mrl) for _ in range(24)])
+        p.add_noise = False
+        clean = p.project(proj, max_ray_length=mrl)
+        lam = p.project_arrays(*[a[None] for a in geo.pose_arrays(proj, [v])], (128, 128), mrl, want="intensity", raw=True)
+    assert np.array_equal(lam[0], clean)
+    d = (noisy - clean)[:, 8:-8, 8:-8]
+    k2 = 0.03**2 + 0.06**2 + 0.02**2 + 0.11**2 + 0.98**2 + 0.11**2 + 0.02**2 + 0.06**2 + 0.03**2
+    # photon_prob ~ transmitted fraction; estimate the expected variance from the clean image itself
+    st = cases.tables([v], "90KV_AL40", None)
+    assert abs(d.mean()) < 3 * d.std() / np.sqrt(d.size) * 6
+    assert np.all(noisy >= 0)
+    rel_var = (d.std(axis=0) / clean[8:-8, 8:-8]) ** 2       # = k2 / (pp * photon_count)
+    pp_est = k2 / (rel_var * 2000.0)
+    assert 0.0 < np.median(pp_est) <= 1.05                    # a transmitted fraction
+    # different seeds give different noise, same seed reproduces
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=proj.intrinsic, add_noise=True, photon_count=2000,
+                   noise_seed=1234) as q:
+        again = q.project(proj, max_ray_length=mrl)
+    assert np.array_equal(again, noisy[0])
+
+
+def test_collected_energy_matches_formula():
+    v = phantoms.c1_volume(32)
+    carm = phantoms.MobileCArmGeometry(sensor_width=48, sensor_height=40, pixel_size=6.0)
+    pose = carm.camera_projection(0.2, -0.1, (0, 0, 0))
+
+    class Dev:
+        source_to_detector_distance = carm.source_to_detector_distance
+        camera_intrinsics = carm.camera_intrinsics
+        detector_height, detector_width = carm.detector_height, carm.detector_width
+
+        def get_camera_projection(self):
+            return pose
+
+    w2i, src, ijk = geo.pose_arrays(pose, [v])
+    with Projector(v, device=Dev(), neglog=False, collected_energy=True, photon_count=5000) as p:
+        ce = p.project()
+        p.collected_energy = False
+        inten = p.project()
+    r = cpu_oracle.project([v.data], cases.tables([v], "90KV_AL40", None).labels, 3, 48, 40, 0.1, w2i, src, ijk, carm.max_ray_length,
+                           *[getattr(cases.tables([v], "90KV_AL40", None), k) for k in ("energies", "pdf", "mu")], want_solid=True)
+    px = carm.source_to_detector_distance / carm.camera_intrinsics.fx
+    expect = inten.astype(np.float64) * r.solid * 5000 / r.solid.astype(np.float64).mean() / (px * px)   # projector.py:846-852
+    assert np.allclose(ce, expect, rtol=2e-5)
+
+
+def test_lifecycle_errors_and_reuse():
+    v = phantoms.c1_volume(16)
+    proj, mrl = phantoms.c1_camera(16)
+    p = Projector(v, camera_intrinsics=proj.intrinsic)
+    with pytest.raises(RuntimeError):
+        p.project(proj)
+    p.initialize()
+    with pytest.raises(RuntimeError):
+        p.initialize()                                        # projector.py:1397-1398
+    with pytest.raises(ValueError):
+        p.project()                                           # no pose and no device (projector.py:632-635)
+    a = p.project(proj, max_ray_length=mrl)
+    assert a.shape == (16, 16)                                # one view -> [H, W] (projector.py:704-705)
+    p.free()
+    p.free()                                                  # idempotent
+    for _ in range(10):                                       # re-create / leak check (tests/test_core.py:896-898)
+        with Projector(v, camera_intrinsics=proj.intrinsic) as q:
+            b = q.project(proj, max_ray_length=mrl)
+        assert np.array_equal(a, b)
