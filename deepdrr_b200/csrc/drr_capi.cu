@@ -3,6 +3,7 @@
 // /root/reference/deepdrr/projector/projector.py (initialize 1395-1717, project 655-800, free 1719-1764).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -377,6 +378,29 @@ int drr_set_mesh_buffers(drr_ctx* c, int layers, int max_hits, const float* hit_
 
 static bool h_has_cells(const drr_ctx* c) { return !c->vols.empty() && c->vols[0].cellcode != nullptr; }
 
+// The warp-cooperative kernel stages the voxel cells an 8x4-pixel tile touches; it pays when neighbouring
+// rays are closer than a few voxels.  Estimate the tile's footprint at the volume centre for view 0 and
+// fall back to the per-ray kernel for coarse detectors / strongly magnified set-ups.
+static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
+    if (c->variant != 0) return c->variant;
+    const VolHost& v = c->vols[0];
+    auto dir = [&](float u, float vv, float* d) {
+        float r[3];
+        for (int a = 0; a < 3; a++) r[a] = u * w2i[3 * a] + vv * w2i[3 * a + 1] + w2i[3 * a + 2];
+        float len = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        for (int a = 0; a < 3; a++) d[a] = (ijk[4 * a] * r[0] + ijk[4 * a + 1] * r[1] + ijk[4 * a + 2] * r[2]) / len;
+    };
+    float d0[3], d1[3];
+    dir(0.5f * W, 0.5f * H, d0);
+    dir(0.5f * W + 8.0f, 0.5f * H + 4.0f, d1);
+    const float ctr[3] = {0.5f * v.ni - src[0], 0.5f * v.nj - src[1], 0.5f * v.nk - src[2]};
+    float dd = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
+    float alpha_c = dd > 0 ? (ctr[0] * d0[0] + ctr[1] * d0[1] + ctr[2] * d0[2]) / dd : 0.0f;
+    float spread = 0.0f;
+    for (int a = 0; a < 3; a++) spread = fmaxf(spread, fabsf(alpha_c * (d1[a] - d0[a])));
+    return spread > 4.0f ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
+}
+
 static int ensure(drr_ctx* c, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes && *p) return DRR_OK;
     cudaFree(*p);
@@ -458,7 +482,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     if (V == 0) {
         CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
     } else if (single) {
-        if (c->variant == 0 && h_has_cells(c)) {
+        if (h_has_cells(c) && pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0) {
             CU(c, drr_launch_march_warp(P, c->n_sm, s));  // persistent: every warp pulls 8x4-pixel tiles from the queue
         } else {
             int occ = drr_march_single_occupancy(M);

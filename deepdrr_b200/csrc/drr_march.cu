@@ -178,8 +178,6 @@ __device__ __forceinline__ int march_ray_single(const MarchParams& P, const View
 template <int NM>
 __global__ void __launch_bounds__(256) march_single_kernel(const __grid_constant__ MarchParams P) {
     const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const bool tex_role = (warp_global & 7) < P.tex_eighths;
     const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
     const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
@@ -195,6 +193,7 @@ __global__ void __launch_bounds__(256) march_single_kernel(const __grid_constant
         const unsigned tv = tile - view * tiles_per_view;
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
         const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
+        const bool tex_role = ((tile * 5u) & 7u) < (unsigned)P.tex_eighths;  // per tile: results independent of scheduling
         if (udx < P.W && vdx < P.H) {
             float acc[NM];
             const ViewDev& vw = P.views[view];

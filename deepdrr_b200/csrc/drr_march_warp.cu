@@ -134,7 +134,22 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
             t += S;
             continue;
         }
-        const int ncell = min(nx * ny * nz, MAXC);  // S == 1 always fits (<= 27 cells); min() is a guard only
+        const int ncell = nx * ny * nz;
+        if (ncell > MAXC) {
+            // Even a single step of this tile does not fit the staging buffer (rays far apart compared with
+            // the voxel size): take the generic per-sample path for this step.  Correct for any geometry;
+            // the host picks the per-ray kernel for such set-ups (drr_capi.cu: pick_variant).
+            w_checkin<NM>(cur, live, acc);
+            for (int s = 0; s < S; s++, t++) {
+                const bool inr = (t < num_steps) && !(alpha < lo) && !(alpha > hi);
+                if (inr) {
+                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
+                    w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);
+                }
+                alpha = __fadd_rn(alpha, step);
+            }
+            continue;
+        }
 
         // ---- 2. stage the cells ----------------------------------------------------------------
         __syncwarp();
@@ -241,8 +256,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) march_warp_kernel(const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
     uint8_t* s_code = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
-    const int warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
-    const bool tex_role = ((warp_global * 5) & 7) < P.tex_eighths;  // spread roles over the warp slots of an SM
     const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
     const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
@@ -259,6 +272,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) march_warp_kernel(const 
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
         const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
         const bool ok = udx < P.W && vdx < P.H;
+        // The sampler is a function of the tile, not of the warp that happens to pull it, so results do
+        // not depend on scheduling; consecutive tiles alternate so every SM runs both kinds at once.
+        const bool tex_role = ((tile * 5u) & 7u) < (unsigned)P.tex_eighths;
         float acc[NM];
         const ViewDev& vw = P.views[view];
         if (tex_role) march_tile<NM, true>(P, vw, udx, vdx, ok, s_coef, s_code, lane, acc, my_steps);

@@ -356,6 +356,12 @@ class Projector(object):
         seed = (self.noise_seed if self.noise_seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFF) + self._noise_calls
         self._noise_calls += 1
         M = len(self.all_materials)
+        if want == "intensity+photon_prob":  # raw kernel outputs (project_kernel.cu:644-645), no post-processing
+            images = np.empty((n, H, W), dtype=np.float32)
+            pprob = np.empty((n, H, W), dtype=np.float32)
+            _lib.check(lib.drr_project(h, n, W, H, _lib.ptr(w2i), _lib.ptr(src), _lib.ptr(ijk), float(self.max_ray_length), 0, 0.0, 0.0, 1.0,
+                                       0, _lib.ptr(images), _lib.ptr(pprob), None, _lib.MEM_HOST), h)
+            return images, pprob
         if want == "intensity":
             images = out if out is not None else np.empty((n, H, W), dtype=np.float32)
             mem = _lib.MEM_DEVICE if hasattr(images, "data_ptr") and images.is_cuda else _lib.MEM_HOST
