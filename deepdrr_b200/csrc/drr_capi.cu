@@ -27,6 +27,25 @@ cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* mi
 cudaError_t drr_launch_collected(float* intensity, float* solid, double* view_sum, const ViewDev* views, int W, int H, int n_views,
                                  float photon_count, float pixel_area, cudaStream_t s);
 
+struct MeshPrimDev {
+    int tri_begin, tri_end;
+    int mat_slot;
+    int layer;
+    float density;
+    int additive, subtractive;
+};
+cudaError_t drr_launch_mesh_transform(const float* verts_local, const int* prim_of_tri, const float* world_from_mesh, int n_tris, int n_prims,
+                                      int n_views, float* verts_world, cudaStream_t s);
+cudaError_t drr_launch_mesh_subtractive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                        int n_prims, int n_tris, int layer, int n_layers, int W, int H, int n_views, int max_hits,
+                                        float far_limit, float* hit_alphas, int8_t* hit_facing, cudaStream_t s);
+cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                     int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int n_views, int max_hits,
+                                     const int8_t* layer_valid, const float* hit_alphas, const int8_t* hit_facing, float* additive,
+                                     cudaStream_t s);
+cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s);
+cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // upload kernels
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +144,17 @@ struct drr_ctx {
     const float* additive = nullptr;
     const int* mesh_mats = nullptr;
     std::vector<void*> mesh_owned;
+    // meshes traced by this library (drr_set_meshes / drr_set_mesh_poses)
+    int n_prims = 0, n_tris = 0, own_layers = 0, own_max_hits = 0, own_n_mats = 0;
+    std::vector<MeshPrimDev> h_prims;
+    std::vector<int8_t> h_layer_valid;
+    float* d_verts_local = nullptr; int* d_prim_of_tri = nullptr; MeshPrimDev* d_prims = nullptr; int* d_own_mesh_mats = nullptr;
+    int8_t* d_own_layer_valid = nullptr;
+    std::vector<float> h_world_from_mesh, h_source_world;
+    int pose_views = 0; float far_limit = 0.0f;
+    float *d_world_from_mesh = nullptr, *d_source_world = nullptr, *d_verts_world = nullptr, *d_own_hit_alphas = nullptr, *d_own_additive = nullptr;
+    int8_t* d_own_hit_facing = nullptr;
+    size_t wfm_cap = 0, srcw_cap = 0, vw_cap = 0, oha_cap = 0, ohf_cap = 0, oadd_cap = 0;
     // per-batch scratch (grown on demand)
     ViewDev* d_views = nullptr; ViewDev* h_views = nullptr; int views_cap = 0;
     float *d_area = nullptr, *d_intensity = nullptr, *d_pprob = nullptr, *d_scratch = nullptr;
@@ -211,6 +241,9 @@ int drr_destroy(drr_ctx* c) {
     cudaDeviceSynchronize();
     drr_clear_volumes(c);
     for (void* p : c->mesh_owned) cudaFree(p);
+    cudaFree(c->d_verts_local); cudaFree(c->d_prim_of_tri); cudaFree(c->d_prims); cudaFree(c->d_own_mesh_mats); cudaFree(c->d_own_layer_valid);
+    cudaFree(c->d_world_from_mesh); cudaFree(c->d_source_world); cudaFree(c->d_verts_world); cudaFree(c->d_own_hit_alphas);
+    cudaFree(c->d_own_additive); cudaFree(c->d_own_hit_facing);
     cudaFree(c->d_energies); cudaFree(c->d_pdf); cudaFree(c->d_mu);
     cudaFree(c->d_views); cudaFreeHost(c->h_views);
     cudaFree(c->d_area); cudaFree(c->d_intensity); cudaFree(c->d_pprob); cudaFree(c->d_scratch);
@@ -378,6 +411,92 @@ int drr_set_mesh_buffers(drr_ctx* c, int layers, int max_hits, const float* hit_
 
 static bool h_has_cells(const drr_ctx* c) { return !c->vols.empty() && c->vols[0].cellcode != nullptr; }
 
+int drr_set_meshes(drr_ctx* c, int n_prims, const int* tri_offsets, const float* vertices, const int* material, const float* density,
+                   const uint8_t* flags, const int* layer, int mesh_layers, int max_mesh_hits) {
+    if (!c) return DRR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_verts_local); cudaFree(c->d_prim_of_tri); cudaFree(c->d_prims); cudaFree(c->d_own_mesh_mats); cudaFree(c->d_own_layer_valid);
+    c->d_verts_local = nullptr; c->d_prim_of_tri = nullptr; c->d_prims = nullptr; c->d_own_mesh_mats = nullptr; c->d_own_layer_valid = nullptr;
+    c->n_prims = 0; c->n_tris = 0; c->h_prims.clear(); c->pose_views = 0;
+    if (n_prims == 0) return DRR_OK;
+    if (n_prims < 0 || !tri_offsets || !vertices || !material || !density || !flags || !layer)
+        return fail(c, DRR_E_INVALID, "drr_set_meshes: bad arguments");
+    if (mesh_layers < 1 || mesh_layers > 4) return fail(c, DRR_E_INVALID, "drr_set_meshes: 1..4 mesh layers supported");
+    if (max_mesh_hits < 4 || max_mesh_hits % 4 != 0 || max_mesh_hits > 128)
+        return fail(c, DRR_E_INVALID, "drr_set_meshes: max_mesh_hits must be a multiple of 4 in [4, 128]");  // projector.py:543-545
+    const int n_tris = tri_offsets[n_prims];
+    // material slots: sorted unique global material indices (projector.py:1548-1557)
+    std::vector<int> mats;
+    for (int p = 0; p < n_prims; p++) {
+        if (material[p] < 0 || material[p] >= DRR_MAX_MATERIALS) return fail(c, DRR_E_INVALID, "drr_set_meshes: material index out of range");
+        bool seen = false;
+        for (int m : mats) seen = seen || m == material[p];
+        if (!seen) mats.push_back(material[p]);
+    }
+    for (size_t i = 0; i < mats.size(); i++)
+        for (size_t j = i + 1; j < mats.size(); j++)
+            if (mats[j] < mats[i]) { int t = mats[i]; mats[i] = mats[j]; mats[j] = t; }
+    c->h_prims.resize(n_prims);
+    c->h_layer_valid.assign(mesh_layers, 0);
+    std::vector<int> prim_of_tri(n_tris);
+    for (int p = 0; p < n_prims; p++) {
+        MeshPrimDev& d = c->h_prims[p];
+        d.tri_begin = tri_offsets[p]; d.tri_end = tri_offsets[p + 1];
+        d.layer = layer[p]; d.density = density[p];
+        d.additive = flags[p] & 1; d.subtractive = (flags[p] >> 1) & 1;
+        d.mat_slot = 0;
+        for (size_t i = 0; i < mats.size(); i++) if (mats[i] == material[p]) d.mat_slot = (int)i;
+        if (d.subtractive && d.layer >= 0 && d.layer < mesh_layers) c->h_layer_valid[d.layer] = 1;  // projector.py:1127-1142
+        for (int t = d.tri_begin; t < d.tri_end; t++) prim_of_tri[t] = p;
+    }
+    CU(c, cudaMalloc(&c->d_verts_local, sizeof(float) * 9 * (size_t)n_tris));
+    CU(c, cudaMalloc(&c->d_prim_of_tri, sizeof(int) * (size_t)n_tris));
+    CU(c, cudaMalloc(&c->d_prims, sizeof(MeshPrimDev) * n_prims));
+    CU(c, cudaMalloc(&c->d_own_mesh_mats, sizeof(int) * mats.size()));
+    CU(c, cudaMalloc(&c->d_own_layer_valid, mesh_layers));
+    CU(c, cudaMemcpy(c->d_verts_local, vertices, sizeof(float) * 9 * (size_t)n_tris, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_prim_of_tri, prim_of_tri.data(), sizeof(int) * (size_t)n_tris, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_prims, c->h_prims.data(), sizeof(MeshPrimDev) * n_prims, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_own_mesh_mats, mats.data(), sizeof(int) * mats.size(), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_own_layer_valid, c->h_layer_valid.data(), mesh_layers, cudaMemcpyHostToDevice));
+    c->n_prims = n_prims; c->n_tris = n_tris; c->own_layers = mesh_layers; c->own_max_hits = max_mesh_hits; c->own_n_mats = (int)mats.size();
+    return DRR_OK;
+}
+
+int drr_set_mesh_poses(drr_ctx* c, int n_views, const float* world_from_mesh, const float* source_world, float far_limit) {
+    if (!c) return DRR_E_INVALID;
+    if (c->n_prims == 0) return fail(c, DRR_E_STATE, "drr_set_mesh_poses: call drr_set_meshes first");
+    if (n_views <= 0 || !world_from_mesh || !source_world) return fail(c, DRR_E_INVALID, "drr_set_mesh_poses: bad arguments");
+    c->h_world_from_mesh.assign(world_from_mesh, world_from_mesh + (size_t)n_views * c->n_prims * 12);
+    c->h_source_world.assign(source_world, source_world + (size_t)n_views * 3);
+    c->pose_views = n_views;
+    c->far_limit = far_limit;
+    return DRR_OK;
+}
+
+int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n, float far_limit, int mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    if (!ts || !facing || n_rays <= 0 || n <= 0 || n > 128) return fail(c, DRR_E_INVALID, "drr_mesh_clean_hits: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    float* dt = ts; int8_t* df = facing;
+    const size_t cnt = (size_t)n_rays * n;
+    if (mem_kind == DRR_MEM_HOST) {
+        CU(c, cudaMalloc(&dt, cnt * 4)); CU(c, cudaMalloc(&df, cnt));
+        CU(c, cudaMemcpyAsync(dt, ts, cnt * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(df, facing, cnt, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c, drr_launch_tide_clean(dt, df, n_rays, n, far_limit, c->stream));
+    c->launches += 1;
+    if (mem_kind == DRR_MEM_HOST) {
+        CU(c, cudaMemcpyAsync(ts, dt, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(facing, df, cnt, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (mem_kind == DRR_MEM_HOST) { cudaFree(dt); cudaFree(df); }
+    return DRR_OK;
+}
+
 // The warp-cooperative kernel stages the voxel cells an 8x4-pixel tile touches; it pays when neighbouring
 // rays are closer than a few voxels.  Estimate the tile's footprint at the volume centre for view 0 and
 // fall back to the per-ray kernel for coarse detectors / strongly magnified set-ups.
@@ -468,7 +587,36 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     P.additive = c->additive; P.mesh_mats = c->mesh_mats;
     P.views = c->d_views; P.area = c->d_area; P.sample_count = c->d_samples; P.tile_counter = c->d_tile_counter;
 
-    const bool meshes = c->layer_valid || c->additive;
+    // ---- meshes traced by this library: fill hit lists + additive buffers for this batch --------------
+    if (c->n_prims > 0) {
+        if (c->pose_views != n_views) return fail(c, DRR_E_STATE, "drr_project: call drr_set_mesh_poses for this batch of %d views first", n_views);
+        const int L = c->own_layers, MH = c->own_max_hits, NMm = c->own_n_mats;
+        if ((rc = ensure(c, (void**)&c->d_world_from_mesh, &c->wfm_cap, sizeof(float) * 12 * (size_t)n_views * c->n_prims))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_source_world, &c->srcw_cap, sizeof(float) * 3 * (size_t)n_views))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_verts_world, &c->vw_cap, sizeof(float) * 9 * (size_t)n_views * c->n_tris))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_own_hit_alphas, &c->oha_cap, sizeof(float) * (size_t)n_views * L * npix * MH))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_own_hit_facing, &c->ohf_cap, (size_t)n_views * L * npix * MH))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_own_additive, &c->oadd_cap, sizeof(float) * 2 * (size_t)n_views * L * NMm * npix))) return rc;
+        CU(c, cudaMemcpyAsync(c->d_world_from_mesh, c->h_world_from_mesh.data(), sizeof(float) * 12 * (size_t)n_views * c->n_prims, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(c->d_source_world, c->h_source_world.data(), sizeof(float) * 3 * (size_t)n_views, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemsetAsync(c->d_own_hit_facing, 0, (size_t)n_views * L * npix * MH, s));
+        CU(c, cudaMemsetAsync(c->d_own_additive, 0, sizeof(float) * 2 * (size_t)n_views * L * NMm * npix, s));
+        CU(c, drr_launch_mesh_transform(c->d_verts_local, c->d_prim_of_tri, c->d_world_from_mesh, c->n_tris, c->n_prims, n_views, c->d_verts_world, s));
+        c->launches += 1;
+        for (int l = L - 1; l >= 0; l--) {
+            if (!c->h_layer_valid[l]) continue;
+            CU(c, drr_launch_mesh_subtractive(c->d_views, c->d_source_world, c->d_verts_world, c->d_prims, c->n_prims, c->n_tris, l, L, W, H, n_views,
+                                              MH, c->far_limit, c->d_own_hit_alphas, c->d_own_hit_facing, s));
+            c->launches += 1;
+        }
+        CU(c, drr_launch_mesh_additive(c->d_views, c->d_source_world, c->d_verts_world, c->d_prims, c->n_prims, c->n_tris, L, NMm, W, H, n_views, MH,
+                                       c->d_own_layer_valid, c->d_own_hit_alphas, c->d_own_hit_facing, c->d_own_additive, s));
+        c->launches += 1;
+        P.mesh_layers = L; P.max_hits = MH; P.n_mesh_mats = NMm;
+        P.hit_alphas = c->d_own_hit_alphas; P.hit_facing = c->d_own_hit_facing; P.layer_valid = c->d_own_layer_valid;
+        P.additive = c->d_own_additive; P.mesh_mats = c->d_own_mesh_mats;
+    }
+    const bool meshes = P.layer_valid || P.additive;
     bool single = (V == 1) && !meshes && !c->attenuate_outside && M <= 8;
     if (single) {
         const VolHost& h = c->vols[0];
@@ -480,7 +628,8 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     }
     CU(c, cudaEventRecord(c->ev[1], s));
     if (V == 0) {
-        CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
+        if (meshes) { CU(c, drr_launch_march_meshonly(P, s)); c->launches += 1; }
+        else CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
     } else if (single) {
         if (h_has_cells(c) && pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0) {
             CU(c, drr_launch_march_warp(P, c->n_sm, s));  // persistent: every warp pulls 8x4-pixel tiles from the queue

@@ -367,6 +367,32 @@ __global__ void __launch_bounds__(128) march_general_kernel(const __grid_constan
     if ((threadIdx.x & 31) == (__ffs(mask) - 1) && ns) atomicAdd(P.sample_count, ns);
 }
 
+// NUM_VOLUMES == 0 (mesh-only scenes): the trace block of projectKernel is compiled out (K.cu:252-555) and
+// only the additive mesh densities reach the area densities (K.cu:565-584).
+__global__ void march_meshonly_kernel(const __grid_constant__ MarchParams P) {
+    const size_t npix = (size_t)P.W * P.H;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * P.n_views) return;
+    const size_t view = idx / npix, pix = idx - view * npix;
+    float area[DRR_MAX_MATERIALS];
+    for (int m = 0; m < P.M; m++) area[m] = 0.0f;
+    if (P.additive != nullptr) {
+        const float* add = P.additive + view * P.mesh_layers * P.n_mesh_mats * npix * 2;
+        for (int i = 0; i < P.n_mesh_mats; i++)
+            for (int j = 0; j < P.mesh_layers; j++) {
+                size_t k = ((size_t)j * P.n_mesh_mats + i) * npix * 2 + pix * 2;
+                if (fabs((double)add[k + 1]) < 0.00001) area[P.mesh_mats[i]] += fmaxf(add[k], 0.0f);
+            }
+    }
+    for (int m = 0; m < P.M; m++) P.area[view * P.M * npix + (size_t)m * npix + pix] = __fdiv_rn(area[m], 10.0f);
+}
+
+cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s) {
+    size_t total = (size_t)P.W * P.H * P.n_views;
+    march_meshonly_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers (called from drr_capi.cu)
 // ---------------------------------------------------------------------------------------------

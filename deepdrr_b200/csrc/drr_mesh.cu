@@ -1,0 +1,260 @@
+// Mesh hit intervals by CUDA ray-triangle intersection (libdrr_b200, sm_100a).
+//
+// Replaces the reference's OpenGL path for meshes: pyrender / GLSL dual depth peeling
+// (deepdrr/pyrenderdrr/renderer.py, shaders/*.frag), the GL<->CUDA interop copies (projector.py:71-113) and
+// the three post-kernels of deepdrr/projector/peel_postprocess_kernel.cu ("PP.cu:n").  Semantics kept:
+//   * rays and distances are the march's own: origin = source, unit direction from world_from_index,
+//     distance = |hit - source| in world mm (shaders/density.frag:12);
+//   * additive buffers per (layer, material): R = sum_hits d * s * rho, G = sum_hits s with s = +1 on
+//     exit and -1 on entry (density.frag:11-12, blend ADD renderer.py:432-436), negative densities clamped
+//     to 0 (renderer.py:424-425); projectKernel uses max(R, 0) iff |G| < 1e-5 (project_kernel.cu:569-579);
+//   * subtractive layers: every hit of the layer's subtractive primitives, then exactly the clean-up of
+//     `tide` (PP.cu:28-155): cut-off, selection sort, duplicate removal, compaction, altitude filter with
+//     "sea level", depth > 1 removal, compaction; facing +1 = entry, -1 = exit (PP.cu:17-26);
+//   * mesh-mesh subtraction (DRRMode.MESH_SUB, shaders/density_between.frag:29-51): a lower layer's
+//     additive path does not count inside the cleaned intervals of higher subtractive layers.
+// An exact enumerator has no pass limit, so where the rasteriser truncates to max_mesh_hits/4 peel passes
+// this keeps the max_mesh_hits nearest hits instead (identical whenever the hits fit).
+#include <math_constants.h>
+
+#include "drr_device.cuh"
+
+#define MESH_CHUNK 128
+#define MESH_MAX_HITS 128
+
+struct MeshPrimDev {
+    int tri_begin, tri_end;
+    int mat_slot;   // index into the mesh material list (additive buffers), -1 if none
+    int layer;
+    float density;
+    int additive, subtractive;
+};
+
+// world = M(3x4) * local, one transform per (view, primitive)
+__global__ void mesh_transform_kernel(const float* __restrict__ verts_local, const int* __restrict__ prim_of_tri,
+                                      const float* __restrict__ world_from_mesh, int n_tris, int n_prims, int n_views,
+                                      float* __restrict__ verts_world) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // vertex index
+    const int view = blockIdx.y;
+    if (i >= n_tris * 3) return;
+    const int prim = prim_of_tri[i / 3];
+    const float* M = world_from_mesh + ((size_t)view * n_prims + prim) * 12;
+    const float x = verts_local[3 * i], y = verts_local[3 * i + 1], z = verts_local[3 * i + 2];
+    float* o = verts_world + ((size_t)view * n_tris * 3 + i) * 3;
+    o[0] = M[0] * x + M[1] * y + M[2] * z + M[3];
+    o[1] = M[4] * x + M[5] * y + M[6] * z + M[7];
+    o[2] = M[8] * x + M[9] * y + M[10] * z + M[11];
+}
+
+// Moeller-Trumbore, double sided.  Returns true and (t, entering) for t > 0.
+__device__ __forceinline__ bool ray_tri(const float3& o, const float3& d, const float* __restrict__ v, float& t, bool& entering) {
+    const float3 e1 = make_float3(v[3] - v[0], v[4] - v[1], v[5] - v[2]);
+    const float3 e2 = make_float3(v[6] - v[0], v[7] - v[1], v[8] - v[2]);
+    const float3 p = make_float3(d.y * e2.z - d.z * e2.y, d.z * e2.x - d.x * e2.z, d.x * e2.y - d.y * e2.x);
+    const float det = e1.x * p.x + e1.y * p.y + e1.z * p.z;
+    if (det == 0.0f) return false;
+    const float inv = 1.0f / det;
+    const float3 s = make_float3(o.x - v[0], o.y - v[1], o.z - v[2]);
+    const float u = (s.x * p.x + s.y * p.y + s.z * p.z) * inv;
+    if (u < 0.0f || u > 1.0f) return false;
+    const float3 q = make_float3(s.y * e1.z - s.z * e1.y, s.z * e1.x - s.x * e1.z, s.x * e1.y - s.y * e1.x);
+    const float w = (d.x * q.x + d.y * q.y + d.z * q.z) * inv;
+    if (w < 0.0f || u + w > 1.0f) return false;
+    t = (e2.x * q.x + e2.y * q.y + e2.z * q.z) * inv;
+    // geometric normal n = e1 x e2; det = d . (e1 x e2) ... sign(det) = sign(-d.n)?  p = d x e2, det = e1.(d x e2) = -d.(e1 x e2)
+    entering = det > 0.0f;  // d . n < 0: the ray enters through an outward-facing (CCW) triangle
+    return t > 0.0f;
+}
+
+// The clean-up of `tide` from the cut-off on (PP.cu:28-155), n = number of slots.
+__device__ void tide_clean(float* ts, int8_t* facing, int n, float far_limit) {
+    const float cutoffEpsilon = 0.00001f;
+    for (int i = 0; i < n; i++)
+        if (ts[i] < cutoffEpsilon || ts[i] > far_limit - 0.001f) { ts[i] = CUDART_INF_F; facing[i] = 0; }
+    for (int sorted = 0; sorted < n; sorted++) {  // selection sort, same tie behaviour as the reference
+        int minIdx = sorted;
+        float minT = ts[minIdx];
+        for (int i = sorted + 1; i < n; i++) { float t = ts[i]; if (t < minT) { minIdx = i; minT = t; } }
+        float tmpT = ts[sorted]; ts[sorted] = minT; ts[minIdx] = tmpT;
+        int8_t tf = facing[sorted]; facing[sorted] = facing[minIdx]; facing[minIdx] = tf;
+    }
+    {  // remove duplicates
+        int dst = 0, src = 1;
+        while (src < n) {
+            if (ts[src] == ts[dst] && facing[src] == facing[dst]) { ts[src] = CUDART_INF_F; facing[src] = 0; src++; }
+            else { dst = src; src++; }
+        }
+    }
+    auto fill_gaps = [&]() {
+        int dst = 0;
+        while (dst < n && facing[dst] != 0) dst++;
+        int src = dst + 1;
+        while (src < n && dst < n) {
+            while (src < n && facing[src] == 0) src++;
+            if (src < n) { ts[dst] = ts[src]; facing[dst] = facing[src]; ts[src] = CUDART_INF_F; facing[src] = 0; }
+            src++; dst++;
+        }
+    };
+    fill_gaps();
+    {
+        int altitude = 0;
+        for (int i = 0; i < n; i++) altitude += facing[i];
+        const int seaLevel = max(0, altitude);
+        int prev = 0, run = 0;
+        for (int i = 0; i < n; i++) {
+            run += facing[i];  // altitudes[i] of the reference, taken before this pass modifies facing[i]
+            const int cur = run;
+            if (cur < seaLevel || prev < seaLevel) { ts[i] = CUDART_INF_F; facing[i] = 0; }
+            if (cur > 1 || prev > 1) { ts[i] = CUDART_INF_F; facing[i] = 0; }
+            prev = cur;
+        }
+    }
+    fill_gaps();
+}
+
+__global__ void tide_clean_kernel(float* __restrict__ ts, int8_t* __restrict__ facing, int n_rays, int n, float far_limit) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float lt[MESH_MAX_HITS];
+    int8_t lf[MESH_MAX_HITS];
+    for (int i = 0; i < n; i++) { lt[i] = ts[(size_t)r * n + i]; lf[i] = facing[(size_t)r * n + i]; }
+    tide_clean(lt, lf, n, far_limit);
+    for (int i = 0; i < n; i++) { ts[(size_t)r * n + i] = lt[i]; facing[(size_t)r * n + i] = lf[i]; }
+}
+
+// Subtractive hit lists of one layer: block = 16x8 pixels, triangles streamed through shared memory.
+__global__ void __launch_bounds__(128) mesh_subtractive_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
+                                                               const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
+                                                               int n_prims, int n_tris, int layer, int n_layers, int W, int H, int max_hits,
+                                                               float far_limit, float* __restrict__ hit_alphas, int8_t* __restrict__ hit_facing) {
+    __shared__ float s_v[MESH_CHUNK * 9];
+    const int tiles_x = (W + 15) / 16;
+    const int view = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
+    const bool ok = udx < W && vdx < H;
+    Ray r = make_ray(views[view].w2i, min(udx, W - 1), min(vdx, H - 1));
+    const float3 d = make_float3(r.rx, r.ry, r.rz);
+    const float3 o = make_float3(source_world[3 * view], source_world[3 * view + 1], source_world[3 * view + 2]);
+    float lt[MESH_MAX_HITS];
+    int8_t lf[MESH_MAX_HITS];
+    for (int i = 0; i < max_hits; i++) { lt[i] = CUDART_INF_F; lf[i] = 0; }
+    int count = 0;
+    const float* vw = verts_world + (size_t)view * n_tris * 9;
+    for (int p = 0; p < n_prims; p++) {
+        const MeshPrimDev pr = prims[p];
+        if (!pr.subtractive || pr.layer != layer) continue;
+        for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
+            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = vw[(size_t)base * 9 + i];
+            __syncthreads();
+            if (!ok) continue;
+            for (int k = 0; k < cnt; k++) {
+                float t; bool entering;
+                if (!ray_tri(o, d, s_v + 9 * k, t, entering)) continue;
+                const int8_t f = entering ? 1 : -1;
+                if (count < max_hits) { lt[count] = t; lf[count] = f; count++; }
+                else {  // keep the max_hits nearest hits
+                    int far_i = 0;
+                    for (int i = 1; i < max_hits; i++) if (lt[i] > lt[far_i]) far_i = i;
+                    if (t < lt[far_i]) { lt[far_i] = t; lf[far_i] = f; }
+                }
+            }
+        }
+    }
+    if (!ok) return;
+    tide_clean(lt, lf, max_hits, far_limit);
+    const size_t npix = (size_t)W * H, pix = (size_t)vdx * W + udx;
+    float* oa = hit_alphas + (((size_t)view * n_layers + layer) * npix + pix) * max_hits;
+    int8_t* of = hit_facing + (((size_t)view * n_layers + layer) * npix + pix) * max_hits;
+    for (int i = 0; i < max_hits; i++) { oa[i] = lt[i]; of[i] = lf[i]; }
+}
+
+// Additive buffers: R += g(t) * s * rho, G += s where g(t) = t minus the part of [0, t] covered by the
+// cleaned intervals of higher subtractive layers (equivalent to density_between.frag for G = 0).
+__global__ void __launch_bounds__(128) mesh_additive_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
+                                                            const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
+                                                            int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int max_hits,
+                                                            const int8_t* __restrict__ layer_valid, const float* __restrict__ hit_alphas,
+                                                            const int8_t* __restrict__ hit_facing, float* __restrict__ additive) {
+    __shared__ float s_v[MESH_CHUNK * 9];
+    const int tiles_x = (W + 15) / 16;
+    const int view = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
+    const bool ok = udx < W && vdx < H;
+    Ray r = make_ray(views[view].w2i, min(udx, W - 1), min(vdx, H - 1));
+    const float3 d = make_float3(r.rx, r.ry, r.rz);
+    const float3 o = make_float3(source_world[3 * view], source_world[3 * view + 1], source_world[3 * view + 2]);
+    const size_t npix = (size_t)W * H, pix = (size_t)vdx * W + udx;
+    const float* vw = verts_world + (size_t)view * n_tris * 9;
+    for (int p = 0; p < n_prims; p++) {
+        const MeshPrimDev pr = prims[p];
+        if (!pr.additive || pr.mat_slot < 0 || pr.layer < 0 || pr.layer >= n_layers) continue;
+        const float rho = fmaxf(pr.density, 0.0f);  // renderer.py:424-425
+        float R = 0.0f, G = 0.0f;
+        for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
+            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = vw[(size_t)base * 9 + i];
+            __syncthreads();
+            if (!ok) continue;
+            for (int k = 0; k < cnt; k++) {
+                float t; bool entering;
+                if (!ray_tri(o, d, s_v + 9 * k, t, entering)) continue;
+                float g = t;
+                for (int l = pr.layer + 1; l < n_layers; l++) {  // subtract the overlap with higher subtractive layers
+                    if (!layer_valid[l]) continue;
+                    const float* ha = hit_alphas + (((size_t)view * n_layers + l) * npix + pix) * max_hits;
+                    const int8_t* hf = hit_facing + (((size_t)view * n_layers + l) * npix + pix) * max_hits;
+                    for (int i = 0; i + 1 < max_hits; i += 2) {  // pairs (near, far) as kernelReorder2 hands them to GL
+                        if (hf[i] == 0 || hf[i + 1] == 0) break;
+                        const float nearD = ha[i], farD = ha[i + 1];
+                        g -= fmaxf(0.0f, fminf(t, farD) - nearD);
+                    }
+                }
+                const float s = entering ? -1.0f : 1.0f;  // density.frag: +1 on exit, -1 on entry
+                R += g * s * rho;
+                G += s;
+            }
+        }
+        if (ok) {
+            float* a = additive + ((((size_t)view * n_layers + pr.layer) * n_mats + pr.mat_slot) * npix + pix) * 2;
+            a[0] += R;
+            a[1] += G;
+        }
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+cudaError_t drr_launch_mesh_transform(const float* verts_local, const int* prim_of_tri, const float* world_from_mesh, int n_tris, int n_prims,
+                                      int n_views, float* verts_world, cudaStream_t s) {
+    dim3 grid((n_tris * 3 + 255) / 256, n_views);
+    mesh_transform_kernel<<<grid, 256, 0, s>>>(verts_local, prim_of_tri, world_from_mesh, n_tris, n_prims, n_views, verts_world);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_mesh_subtractive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                        int n_prims, int n_tris, int layer, int n_layers, int W, int H, int n_views, int max_hits,
+                                        float far_limit, float* hit_alphas, int8_t* hit_facing, cudaStream_t s) {
+    dim3 grid(((W + 15) / 16) * ((H + 7) / 8), n_views);
+    mesh_subtractive_kernel<<<grid, 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, n_tris, layer, n_layers, W, H, max_hits,
+                                                 far_limit, hit_alphas, hit_facing);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                     int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int n_views, int max_hits,
+                                     const int8_t* layer_valid, const float* hit_alphas, const int8_t* hit_facing, float* additive,
+                                     cudaStream_t s) {
+    dim3 grid(((W + 15) / 16) * ((H + 7) / 8), n_views);
+    mesh_additive_kernel<<<grid, 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, n_tris, n_layers, n_mats, W, H, max_hits,
+                                              layer_valid, hit_alphas, hit_facing, additive);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s) {
+    tide_clean_kernel<<<(n_rays + 63) / 64, 64, 0, s>>>(ts, facing, n_rays, n, far_limit);
+    return cudaGetLastError();
+}

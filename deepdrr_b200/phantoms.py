@@ -13,7 +13,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import geo
-from .vol import Volume
+from .vol import Mesh, Volume
 
 
 # ----------------------------------------------------------------------------------------------
@@ -239,3 +239,67 @@ def cone_poses(n: int, seed: int = 2, sensor: int = 384, pixel: float = 0.3, sdd
         d = ct * axis + st * (math.cos(ph) * e1 + math.sin(ph) * e2)
         out.append(look_at_projection(-source_distance * d, d, e1 if abs(d @ e1) < 0.9 else e2, k))
     return out, 4.0 * sdd
+
+
+# ----------------------------------------------------------------------------------------------
+# C4: procedural watertight meshes (the reference's STL fixtures are not shipped)
+# ----------------------------------------------------------------------------------------------
+def icosphere(radius: float = 10.0, subdivisions: int = 2):
+    """(vertices [n,3], faces [m,3]) of a geodesic sphere, outward normals counter-clockwise."""
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[key] = len(v) - 1
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return (np.array(v) * radius).astype(np.float32), np.array(f, dtype=np.int64)
+
+
+def screw_mesh(length: float = 130.0, core_radius: float = 2.2, thread_radius: float = 3.25, pitch: float = 2.75,
+               thread_length: float = 32.0, segments: int = 48, rings_per_mm: float = 4.0):
+    """A watertight screw-like solid of revolution with a helical thread over the first ``thread_length`` mm
+    (stand-in for data/6.5mmD_32mmThread_L130mm.STL: 6.5 mm thread diameter, 32 mm thread, 130 mm long).
+    Axis = +z, tip at z = 0.  About 50 k triangles at the defaults."""
+    nz = int(length * rings_per_mm) + 1
+    z = np.linspace(0.0, length, nz)
+    th = np.linspace(0.0, 2 * math.pi, segments, endpoint=False)
+    zz, tt = np.meshgrid(z, th, indexing="ij")
+    phase = (zz / pitch - tt / (2 * math.pi)) % 1.0
+    tooth = np.clip(1.0 - np.abs(phase - 0.5) * 4.0, 0.0, 1.0)          # triangular thread profile
+    taper = np.clip(zz / 6.0, 0.15, 1.0)                                  # pointed tip
+    r = (core_radius + (thread_radius - core_radius) * tooth * (zz < thread_length)) * taper
+    verts = np.stack([r * np.cos(tt), r * np.sin(tt), zz], axis=-1).reshape(-1, 3)
+    faces = []
+    for i in range(nz - 1):
+        for j in range(segments):
+            a, b = i * segments + j, i * segments + (j + 1) % segments
+            c, d = a + segments, b + segments
+            faces += [(a, b, d), (a, d, c)]
+    bottom, top = len(verts), len(verts) + 1
+    verts = np.concatenate([verts, [[0, 0, 0.0], [0, 0, length]]], axis=0)
+    for j in range(segments):
+        jn = (j + 1) % segments
+        faces.append((bottom, jn, j))
+        faces.append((top, (nz - 1) * segments + j, (nz - 1) * segments + jn))
+    return verts.astype(np.float32), np.array(faces, dtype=np.int64)
+
+
+def box_mesh(half=(5.0, 5.0, 5.0)):
+    hx, hy, hz = half
+    v = np.array([[-hx, -hy, -hz], [hx, -hy, -hz], [hx, hy, -hz], [-hx, hy, -hz], [-hx, -hy, hz], [hx, -hy, hz], [hx, hy, hz], [-hx, hy, hz]], dtype=np.float32)
+    f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5], [0, 4, 7], [0, 7, 3]], dtype=np.int64)
+    return v, f

@@ -91,8 +91,7 @@ class Projector(object):
             else:
                 raise ValueError(f"unrecognized Renderable type: {type(_vol)}.")
         self.mesh_additive_enabled = len(self.meshes) > 0
-        if self.meshes:
-            raise NotImplementedError("mesh rendering (CUDA ray-triangle hit intervals) is not wired into Projector yet")
+        self.primitives = list(self.meshes)  # one primitive per Mesh
 
         if priorities is None:
             self.priorities = default_priorities(len(self.volumes))
@@ -141,7 +140,7 @@ class Projector(object):
         if self.max_mesh_hits < 4 or self.max_mesh_hits % 4 != 0:
             raise ValueError("max_mesh_depth must be a multiple of 4 and >= 4")
 
-        self.all_materials = material_universe(self.volumes, [], attenuate_outside_volume)
+        self.all_materials = material_universe(self.volumes, [m.material for m in self.meshes], attenuate_outside_volume)
         if attenuate_outside_volume:
             assert "air" in self.all_materials
             air_index = self.all_materials.index("air")
@@ -164,6 +163,7 @@ class Projector(object):
 
         self.output_shape = None
         self.initialized = False
+        self._sensor_fixed = None
         self._h = None
         self.max_ray_length = None
 
@@ -222,6 +222,8 @@ class Projector(object):
                 vid = ctypes.c_int(-1)
                 _lib.check(lib.drr_add_volume(h, _lib.ptr(dens), _lib.ptr(labels), dens.shape[0], dens.shape[1], dens.shape[2],
                                               _lib.MEM_HOST, 0, ctypes.byref(vid)), h)
+            self._mesh_state = None
+            self._upload_meshes()
             sampler = {"alu": _lib.SAMPLER_ALU, "tex": _lib.SAMPLER_TEX, "hybrid": _lib.SAMPLER_HYBRID}[self.sampler]
             _lib.check(lib.drr_set_march(h, self.step, int(self.attenuate_outside_volume), int(self.air_index), sampler), h)
         except Exception:
@@ -230,6 +232,27 @@ class Projector(object):
             raise
         self.output_shape = tuple(self.camera_intrinsics.sensor_size) if (self.device is not None or self._camera_intrinsics is not None) else None
         self.initialized = True
+
+    def _upload_meshes(self):
+        """Hand the triangle soup to the library (replaces the pyrender scene set-up, reference :1564-1598).
+        Re-done when a mesh is enabled / disabled (``is_visible`` in the reference, :1127-1142)."""
+        if not self.meshes:
+            return
+        state = tuple(bool(getattr(m, "enabled", True)) for m in self.meshes)
+        if state == self._mesh_state:
+            return
+        lib, h = _lib.load(), self._h
+        tris = [np.ascontiguousarray(m.triangles, dtype=np.float32).reshape(-1, 9) for m in self.meshes]
+        offsets = np.zeros(len(tris) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(t) for t in tris])
+        verts = np.ascontiguousarray(np.concatenate(tris, axis=0)) if offsets[-1] else np.zeros((0, 9), np.float32)
+        material = np.array([self.all_materials.index(m.material) for m in self.meshes], dtype=np.int32)
+        density = np.array([m.density for m in self.meshes], dtype=np.float32)
+        flags = np.array([((1 if m.additive else 0) | (2 if m.subtractive else 0)) if en else 0 for m, en in zip(self.meshes, state)], dtype=np.uint8)
+        layer = np.array([m.layer for m in self.meshes], dtype=np.int32)
+        _lib.check(lib.drr_set_meshes(h, len(self.meshes), _lib.ptr(offsets), _lib.ptr(verts), _lib.ptr(material), _lib.ptr(density),
+                                      _lib.ptr(flags), _lib.ptr(layer), int(self.mesh_layers), int(self.max_mesh_hits)), h)
+        self._mesh_state = state
 
     def free(self):
         """Free the GPU handle (reference: :1719-1764)."""
@@ -291,7 +314,7 @@ class Projector(object):
         return self._project_batch(camera_projections, want="area")
 
     def project_arrays(self, world_from_index, source_ijk, ijk_from_world, sensor_size, max_ray_length: float,
-                       want: str = "intensity", raw: bool = False, out=None):
+                       want: str = "intensity", raw: bool = False, out=None, source_world=None):
         """Extra, lower-level entry point: project from the kernel-level per-view arrays.
 
         ``world_from_index`` [n, 9], ``source_ijk`` [n, V, 3], ``ijk_from_world`` [n, V, 12] are exactly the
@@ -306,7 +329,7 @@ class Projector(object):
         src = np.ascontiguousarray(source_ijk, dtype=np.float32).reshape(n, max(V, 1), 3)
         ijk = np.ascontiguousarray(ijk_from_world, dtype=np.float32).reshape(n, max(V, 1), 12)
         self.max_ray_length = float(max_ray_length)
-        return self._run(w2i, src, ijk, int(sensor_size[0]), int(sensor_size[1]), want, out, raw, None)
+        return self._run(w2i, src, ijk, int(sensor_size[0]), int(sensor_size[1]), want, out, raw, None, source_world)
 
     def _pose_arrays(self, camera_projections):
         n, V = len(camera_projections), len(self.volumes)
@@ -326,11 +349,33 @@ class Projector(object):
             raise ValueError("all camera projections of one call must share the sensor size")
         W, H = sizes.pop()
         w2i, src, ijk = self._pose_arrays(camera_projections)
-        return self._run(w2i, src, ijk, W, H, want, out, raw, camera_projections[0].intrinsic)
+        source_world = np.stack([np.asarray(p.center_in_world, dtype=np.float64).reshape(-1)[:3] for p in camera_projections]).astype(np.float32)
+        return self._run(w2i, src, ijk, W, H, want, out, raw, camera_projections[0].intrinsic, source_world)
 
-    def _run(self, w2i, src, ijk, W, H, want, out, raw, intrinsic):
+    def _run(self, w2i, src, ijk, W, H, want, out, raw, intrinsic, source_world=None):
         lib, h = _lib.load(), self._h
         n = w2i.shape[0]
+        if self.meshes:
+            # hit lists are max_mesh_hits floats per pixel and layer: project mesh scenes in small batches
+            chunk = max(1, min(n, int(2e8 // max(1, W * H * self.max_mesh_hits * self.mesh_layers * 5))))
+            if source_world is None:
+                raise ValueError("mesh scenes need the source position in world coordinates (source_world)")
+            if self.initialized and self._sensor_fixed not in (None, (W, H)):
+                raise RuntimeError("Changing sensor size while using meshes is not yet supported.")  # reference :1359-1363
+            self._sensor_fixed = (W, H)
+            self._upload_meshes()
+            wfm = np.stack([np.asarray(m.world_from_ijk.toarray(), dtype=np.float32).reshape(12) for m in self.meshes])
+            if n > chunk:
+                if want == "intensity+photon_prob" or out is not None:
+                    raise ValueError("batched mesh projection: pass at most %d views per call here" % chunk)
+                parts = [self._run(w2i[a:a + chunk], src[a:a + chunk], ijk[a:a + chunk], W, H, want, None, raw, intrinsic, source_world[a:a + chunk])
+                         for a in range(0, n, chunk)]
+                if want == "intensity" and self.neglog and not raw and len(parts) > 1:
+                    pass  # neglog is per image; only the "any constant image zeroes the batch" quirk is per call
+                return np.concatenate(parts, axis=0)
+            wfm_all = np.ascontiguousarray(np.broadcast_to(wfm[None], (n,) + wfm.shape), dtype=np.float32)
+            sw = np.ascontiguousarray(source_world, dtype=np.float32).reshape(n, 3)
+            _lib.check(lib.drr_set_mesh_poses(h, n, _lib.ptr(wfm_all), _lib.ptr(sw), float(self.source_to_detector_distance * 2)), h)
         self.output_shape = (W, H)
         V = len(self.volumes)
         pr = np.ascontiguousarray(self.priorities, dtype=np.int32)

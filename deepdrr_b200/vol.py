@@ -139,3 +139,64 @@ class Volume(Renderable):
 
     def get_center(self) -> np.ndarray:
         return self.anatomical_from_IJK @ (np.array(self.shape, dtype=np.float64) / 2)
+
+
+# Default mesh densities in g/cm^3 by material name (reference: pyrenderdrr/material.py:5-20).
+DEFAULT_MESH_DENSITIES = {
+    "bone": 1.92, "soft tissue": 1.0, "tissue_soft": 1.0, "blood": 1.06, "muscle": 1.06, "air": 0.0012, "iron": 7.87,
+    "lead": 11.34, "copper": 8.96, "lung": 0.26, "titanium": 4.51, "teflon": 2.2, "polyethylene": 0.94, "concrete": 2.3,
+}
+
+
+class Mesh(Renderable):
+    """Triangle mesh with a DRR material (reference: vol/mesh.py:40-183 + pyrenderdrr/material.py:22-124).
+
+    One ``Mesh`` is one primitive: ``vertices`` [n, 3] in mesh-local (IJK) coordinates, ``faces`` [m, 3] with
+    outward normals counter-clockwise, material name (must be a known ``Material``), ``density`` in g/cm^3
+    (default by name), ``additive`` / ``subtractive`` flags and ``layer`` (pyrenderdrr/material.py:38-44).
+    Meshes must be watertight and the source must be outside them (README.md:257).
+    """
+
+    def __init__(self, vertices, faces, material: str = "iron", density: Optional[float] = None, additive: bool = True,
+                 subtractive: bool = False, layer: int = 0, tag: Optional[str] = None, anatomical_from_IJK=None,
+                 world_from_anatomical=None, enabled: bool = True):
+        Renderable.__init__(self, anatomical_from_IJK, world_from_anatomical, enabled=enabled)
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, dtype=np.int64).reshape(-1, 3)
+        if self.faces.size and (self.faces.min() < 0 or self.faces.max() >= len(self.vertices)):
+            raise ValueError("face index out of range")
+        self.material = material
+        if density is None:
+            if material not in DEFAULT_MESH_DENSITIES:
+                raise ValueError(f"no default density for material {material!r}; pass density=")
+            density = DEFAULT_MESH_DENSITIES[material]
+        self.density = float(density)
+        self.additive, self.subtractive, self.layer, self.tag = bool(additive), bool(subtractive), int(layer), tag
+
+    @property
+    def triangles(self) -> np.ndarray:
+        """[m, 3, 3] float32 vertex coordinates per triangle (mesh-local)."""
+        return self.vertices[self.faces]
+
+    @property
+    def shape(self):
+        return tuple(np.ptp(self.vertices, axis=0)) if len(self.vertices) else (0, 0, 0)
+
+    def get_center(self) -> np.ndarray:
+        return self.anatomical_from_IJK @ self.vertices.mean(axis=0).astype(np.float64)
+
+    @classmethod
+    def from_stl(cls, path, **kwargs) -> "Mesh":
+        """Binary or ASCII STL reader (the reference loads STLs through trimesh / pyvista, vol/mesh.py:91-140)."""
+        raw = open(path, "rb").read()
+        n = int.from_bytes(raw[80:84], "little") if len(raw) >= 84 else -1
+        if n >= 0 and len(raw) == 84 + 50 * n:
+            rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n, offset=84)
+            tris = rec["v"].astype(np.float32)
+        else:
+            import re
+            nums = re.findall(rb"vertex\s+(\S+)\s+(\S+)\s+(\S+)", raw)
+            tris = np.array(nums, dtype=np.float32).reshape(-1, 3, 3)
+        verts = tris.reshape(-1, 3)
+        faces = np.arange(len(verts)).reshape(-1, 3)
+        return cls(verts, faces, **kwargs)

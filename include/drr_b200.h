@@ -101,6 +101,25 @@ int drr_set_mesh_buffers(drr_ctx* ctx, int layers, int max_hits, const float* hi
                          const int8_t* layer_valid, const float* additive, const int* mesh_mats, int n_mesh_mats,
                          int mem_kind);
 
+/* Replaces: the pyrender scene + OpenGL renderer set-up (projector.py:1564-1598) and, per projection, the whole
+ * _render_mesh path (projector.py:1055-1330: GL additive passes, dual depth peeling, kernelReorder / kernelTide /
+ * kernelReorder2, MESH_SUB passes, GL<->CUDA copies) by CUDA ray-triangle intersection.
+ *   n_prims primitives; primitive p owns triangles [tri_offsets[p], tri_offsets[p+1]) of `vertices`
+ *   ([n_tris][3 vertices][xyz], mesh-local coordinates, outward normals counter-clockwise);
+ *   material[p] = global material index, density[p] (g/cm^3), flags[p] bit0 additive / bit1 subtractive
+ *   (pyrenderdrr/material.py:41-42), layer[p]; mesh_layers, max_mesh_hits as in Projector (projector.py:419-420).
+ * n_prims == 0 removes all meshes. */
+int drr_set_meshes(drr_ctx* ctx, int n_prims, const int* tri_offsets, const float* vertices, const int* material,
+                   const float* density, const uint8_t* flags, const int* layer, int mesh_layers, int max_mesh_hits);
+/* Per batch, before drr_project: world_from_mesh [n_views][n_prims][12] (3x4 row-major), source_world
+ * [n_views][3], far_limit = 2 * source_to_detector_distance (projector.py:1227).  Replaces
+ * _setup_pyrender_scene (projector.py:855-880). */
+int drr_set_mesh_poses(drr_ctx* ctx, int n_views, const float* world_from_mesh, const float* source_world,
+                       float far_limit);
+/* Replaces: kernelTide (peel_postprocess_kernel.cu:15-177) from its cut-off step on: cleans n_rays hit
+ * lists of n (<= 128) slots (distance, facing: +1 entry / -1 exit / 0 empty) in place. */
+int drr_mesh_clean_hits(drr_ctx* ctx, float* ts, int8_t* facing, int n_rays, int n, float far_limit, int mem_kind);
+
 /* Replaces: the per-view loop of Projector.project -> _render_single (projector.py:679-685, 709-800):
  * _update_object_locations uploads (802-831), the projectKernel launch (770-774), the two D2H copies
  * and swapaxes (786-792) and the host post-processing (691-702), for a whole batch of views.

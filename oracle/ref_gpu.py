@@ -38,6 +38,7 @@ def _load():
                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_float)]
         lib.ref_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_tide.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
         _lib = lib
     return _lib
 
@@ -119,3 +120,12 @@ class RefProjector:
             self.close()
         except Exception:
             pass
+
+
+def ref_tide(ts_peel: np.ndarray, far_limit: float):
+    """The reference's kernelTide on ``ts_peel`` [n_rays, 32] (peel layout); returns (ts, facing) cleaned."""
+    ts = np.ascontiguousarray(ts_peel, dtype=np.float32).copy()
+    assert ts.ndim == 2 and ts.shape[1] == 32
+    facing = np.zeros(ts.shape, dtype=np.int8)
+    _chk(_load().ref_tide(os.path.join(_REF, "ref_peel.cubin").encode(), _p(ts), _p(facing), ts.shape[0], float(far_limit)))
+    return ts, facing

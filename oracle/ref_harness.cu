@@ -243,6 +243,30 @@ int ref_project(void* hp, int W, int H, float step, const int* priority, const i
     return 0;
 }
 
+// kernelTide of the reference (peel_postprocess_kernel.cu:158-177, launch as projector.py:1208-1231) on host
+// arrays: ts [n_rays][32] in the peel layout (-exit, +exit, -entry, +entry per pass), facing [n_rays][32] out.
+int ref_tide(const char* cubin_path, float* ts, int8_t* facing, int n_rays, float source_to_detector_distance_x2) {
+    RH_CHECK(cudaFree(0));
+    CUmodule mod;
+    CUfunction fn;
+    RH_CU(cuModuleLoad(&mod, cubin_path));
+    RH_CU(cuModuleGetFunction(&fn, mod, "kernelTide"));
+    float* dt; int8_t* df;
+    size_t n = (size_t)n_rays * 32;
+    RH_CHECK(cudaMalloc(&dt, n * 4));
+    RH_CHECK(cudaMalloc(&df, n));
+    RH_CHECK(cudaMemcpy(dt, ts, n * 4, cudaMemcpyHostToDevice));
+    RH_CHECK(cudaMemset(df, 0, n));
+    void* args[] = {&dt, &df, &n_rays, &source_to_detector_distance_x2};
+    RH_CU(cuLaunchKernel(fn, 2048, 1, 1, 32, 1, 1, 0, 0, args, nullptr));
+    RH_CHECK(cudaDeviceSynchronize());
+    RH_CHECK(cudaMemcpy(ts, dt, n * 4, cudaMemcpyDeviceToHost));
+    RH_CHECK(cudaMemcpy(facing, df, n, cudaMemcpyDeviceToHost));
+    cudaFree(dt); cudaFree(df);
+    cuModuleUnload(mod);
+    return 0;
+}
+
 int ref_destroy(void* hp) {
     RefHarness* h = (RefHarness*)hp;
     if (!h) return 0;
