@@ -46,6 +46,34 @@ cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_w
 cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s);
 cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s);
 
+struct ScatterTables {
+    int n_mat, n_e;
+    float e0, de;
+    const float* mfp;
+    const float* rita;
+    const float* compton;
+    const int* nshell;
+    const float* inv_rho_nom;
+    const float* majorant;
+    const int* mat_of_label;
+};
+struct ScatterParams {
+    ScatterTables T;
+    VolDev vol;
+    float ijk[12];
+    float p_idx[12];
+    float w2i[9];
+    float src[3];
+    int W, H;
+    int n_bins;
+    const float* spec_e_keV;
+    const float* spec_cdf;
+    unsigned long long n_photons, photon_offset, seed;
+    unsigned long long* tally;
+    double* counters;
+};
+cudaError_t drr_launch_scatter(const ScatterParams& P, int n_sm, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // upload kernels
 // ---------------------------------------------------------------------------------------------
@@ -152,6 +180,12 @@ struct drr_ctx {
     int8_t* d_own_layer_valid = nullptr;
     std::vector<float> h_world_from_mesh, h_source_world;
     int pose_views = 0; float far_limit = 0.0f;
+    // scatter
+    std::vector<float> h_energies, h_pdf;
+    ScatterTables sc = {};
+    bool sc_ready = false;
+    float* d_sc_cdf = nullptr; unsigned long long* d_sc_tally = nullptr; double* d_sc_counters = nullptr; size_t sc_tally_cap = 0;
+    std::vector<void*> sc_owned;
     float *d_world_from_mesh = nullptr, *d_source_world = nullptr, *d_verts_world = nullptr, *d_own_hit_alphas = nullptr, *d_own_additive = nullptr;
     int8_t* d_own_hit_facing = nullptr;
     size_t wfm_cap = 0, srcw_cap = 0, vw_cap = 0, oha_cap = 0, ohf_cap = 0, oadd_cap = 0;
@@ -177,6 +211,10 @@ static int fail(drr_ctx* c, int code, const char* fmt, ...) {
     va_end(ap);
     if (c) c->err = buf; else g_create_err = buf;
     return code;
+}
+
+extern "C" {
+static int ensure(drr_ctx* c, void** p, size_t* cap, size_t bytes);
 }
 
 #define CU(c, x)                                                                                     \
@@ -241,6 +279,8 @@ int drr_destroy(drr_ctx* c) {
     cudaDeviceSynchronize();
     drr_clear_volumes(c);
     for (void* p : c->mesh_owned) cudaFree(p);
+    for (void* p : c->sc_owned) cudaFree(p);
+    cudaFree(c->d_sc_cdf); cudaFree(c->d_sc_tally); cudaFree(c->d_sc_counters);
     cudaFree(c->d_verts_local); cudaFree(c->d_prim_of_tri); cudaFree(c->d_prims); cudaFree(c->d_own_mesh_mats); cudaFree(c->d_own_layer_valid);
     cudaFree(c->d_world_from_mesh); cudaFree(c->d_source_world); cudaFree(c->d_verts_world); cudaFree(c->d_own_hit_alphas);
     cudaFree(c->d_own_additive); cudaFree(c->d_own_hit_facing);
@@ -283,6 +323,8 @@ int drr_set_spectrum(drr_ctx* c, int n_bins, int M, const float* energies, const
     CU(c, cudaMemcpy(c->d_mu, mu, sizeof(float) * (size_t)n_bins * M, cudaMemcpyHostToDevice));
     c->n_bins = n_bins;
     c->M = M;
+    c->h_energies.assign(energies, energies + n_bins);
+    c->h_pdf.assign(pdf, pdf + n_bins);
     return DRR_OK;
 }
 
@@ -472,6 +514,96 @@ int drr_set_mesh_poses(drr_ctx* c, int n_views, const float* world_from_mesh, co
     c->h_source_world.assign(source_world, source_world + (size_t)n_views * 3);
     c->pose_views = n_views;
     c->far_limit = far_limit;
+    return DRR_OK;
+}
+
+int drr_set_scatter_tables(drr_ctx* c, int n_mat, int n_e, float e0, float de, const float* mfp, const float* rita, const float* compton,
+                           const int* nshell, const float* rho_nom, const int* mat_of_label, const float* rho_max_of_label) {
+    if (!c) return DRR_E_INVALID;
+    if (c->M == 0) return fail(c, DRR_E_STATE, "drr_set_scatter_tables: call drr_set_spectrum first");
+    if (n_mat <= 0 || n_e < 2 || !mfp || !rita || !compton || !nshell || !rho_nom || !mat_of_label || !rho_max_of_label)
+        return fail(c, DRR_E_INVALID, "drr_set_scatter_tables: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (void* p : c->sc_owned) cudaFree(p);
+    c->sc_owned.clear();
+    c->sc_ready = false;
+    std::vector<float> inv_rho(n_mat), maj(n_e, 0.0f);
+    for (int m = 0; m < n_mat; m++) inv_rho[m] = 1.0f / rho_nom[m];
+    for (int l = 0; l < c->M; l++) {
+        int m = mat_of_label[l];
+        if (m < 0 || m >= n_mat) return fail(c, DRR_E_INVALID, "drr_set_scatter_tables: material %d has no MC table", l);
+        for (int e = 0; e < n_e; e++) {
+            float mu = rho_max_of_label[l] * inv_rho[m] / mfp[((size_t)m * n_e + e) * 5 + 3];
+            if (mu > maj[e]) maj[e] = mu;
+        }
+    }
+    for (int e = 0; e < n_e; e++) if (!(maj[e] > 0.0f)) maj[e] = 1e-6f;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        CU(c, cudaMalloc(&d, bytes));
+        c->sc_owned.push_back(d);
+        CU(c, cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        *dst = d;
+        return DRR_OK;
+    };
+    int rc;
+    const void* p;
+    if ((rc = up(mfp, sizeof(float) * 5 * (size_t)n_mat * n_e, &p))) return rc; c->sc.mfp = (const float*)p;
+    if ((rc = up(rita, sizeof(float) * 4 * 128 * (size_t)n_mat, &p))) return rc; c->sc.rita = (const float*)p;
+    if ((rc = up(compton, sizeof(float) * 3 * 30 * (size_t)n_mat, &p))) return rc; c->sc.compton = (const float*)p;
+    if ((rc = up(nshell, sizeof(int) * n_mat, &p))) return rc; c->sc.nshell = (const int*)p;
+    if ((rc = up(inv_rho.data(), sizeof(float) * n_mat, &p))) return rc; c->sc.inv_rho_nom = (const float*)p;
+    if ((rc = up(maj.data(), sizeof(float) * n_e, &p))) return rc; c->sc.majorant = (const float*)p;
+    if ((rc = up(mat_of_label, sizeof(int) * c->M, &p))) return rc; c->sc.mat_of_label = (const int*)p;
+    c->sc.n_mat = n_mat; c->sc.n_e = n_e; c->sc.e0 = e0; c->sc.de = de;
+    // spectrum CDF of max(pdf, 0) (the last bin of the reference's spectra is negative)
+    std::vector<float> cdf(c->n_bins);
+    double tot = 0.0;
+    for (int b = 0; b < c->n_bins; b++) tot += c->h_pdf[b] > 0 ? c->h_pdf[b] : 0.0;
+    double run = 0.0;
+    for (int b = 0; b < c->n_bins; b++) { run += c->h_pdf[b] > 0 ? c->h_pdf[b] : 0.0; cdf[b] = (float)(run / tot); }
+    cdf[c->n_bins - 1] = 1.0f;
+    cudaFree(c->d_sc_cdf); c->d_sc_cdf = nullptr;
+    CU(c, cudaMalloc(&c->d_sc_cdf, sizeof(float) * c->n_bins));
+    CU(c, cudaMemcpy(c->d_sc_cdf, cdf.data(), sizeof(float) * c->n_bins, cudaMemcpyHostToDevice));
+    if (!c->d_sc_counters) CU(c, cudaMalloc(&c->d_sc_counters, sizeof(double) * 8));
+    c->sc_ready = true;
+    return DRR_OK;
+}
+
+int drr_scatter(drr_ctx* c, unsigned long long n_photons, unsigned long long photon_offset, uint64_t seed, int W, int H, const float* w2i,
+                const float* index_from_world, const float* source_world, const float* ijk_from_world, unsigned long long* out_tally,
+                double* out_counters, int out_mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    if (!c->sc_ready) return fail(c, DRR_E_STATE, "drr_scatter: call drr_set_scatter_tables first");
+    if (c->vols.size() != 1 || !c->vols[0].dens) return fail(c, DRR_E_INVALID, "drr_scatter: exactly one volume is supported");
+    if (W <= 0 || H <= 0 || !w2i || !index_from_world || !source_world || !ijk_from_world || !out_tally)
+        return fail(c, DRR_E_INVALID, "drr_scatter: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t npix = (size_t)W * H;
+    int rc;
+    if ((rc = ensure(c, (void**)&c->d_sc_tally, &c->sc_tally_cap, sizeof(unsigned long long) * npix))) return rc;
+    CU(c, cudaMemsetAsync(c->d_sc_tally, 0, sizeof(unsigned long long) * npix, s));
+    CU(c, cudaMemsetAsync(c->d_sc_counters, 0, sizeof(double) * 8, s));
+    ScatterParams P;
+    memset(&P, 0, sizeof P);
+    P.T = c->sc;
+    const VolHost& h = c->vols[0];
+    P.vol.dens = h.dens; P.vol.lab = h.lab; P.vol.ni = h.ni; P.vol.nj = h.nj; P.vol.nk = h.nk;
+    memcpy(P.ijk, ijk_from_world, 48); memcpy(P.p_idx, index_from_world, 48); memcpy(P.w2i, w2i, 36); memcpy(P.src, source_world, 12);
+    P.W = W; P.H = H; P.n_bins = c->n_bins; P.spec_e_keV = c->d_energies; P.spec_cdf = c->d_sc_cdf;
+    P.n_photons = n_photons; P.photon_offset = photon_offset; P.seed = seed;
+    P.tally = c->d_sc_tally; P.counters = c->d_sc_counters;
+    CU(c, cudaEventRecord(c->ev[1], s));
+    if (n_photons > 0) { CU(c, drr_launch_scatter(P, c->n_sm, s)); c->launches += 1; }
+    CU(c, cudaEventRecord(c->ev[2], s));
+    const cudaMemcpyKind kind = out_mem_kind == DRR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CU(c, cudaMemcpyAsync(out_tally, c->d_sc_tally, sizeof(unsigned long long) * npix, kind, s));
+    if (out_counters) CU(c, cudaMemcpyAsync(out_counters, c->d_sc_counters, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    CU(c, cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]));
     return DRR_OK;
 }
 
@@ -694,6 +826,49 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     CU(c, cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]));
     CU(c, cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]));
     CU(c, cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[4]));
+    return DRR_OK;
+}
+
+int drr_postprocess(drr_ctx* c, float* images, const float* photon_prob, int n_views, int W, int H, unsigned post_flags, float photon_count,
+                    float intensity_upper_bound, uint64_t seed, int mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    if (!images || n_views <= 0 || W <= 0 || H <= 0) return fail(c, DRR_E_INVALID, "drr_postprocess: bad arguments");
+    if ((post_flags & DRR_POST_NOISE) && !photon_prob) return fail(c, DRR_E_INVALID, "drr_postprocess: noise needs photon_prob");
+    if (post_flags & DRR_POST_COLLECTED) return fail(c, DRR_E_INVALID, "drr_postprocess: collected energy is only available in drr_project");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t npix = (size_t)W * H, total = npix * n_views;
+    int rc;
+    float* d_img = images;
+    const float* d_pp = photon_prob;
+    if (mem_kind == DRR_MEM_HOST) {
+        if ((rc = ensure(c, (void**)&c->d_intensity, &c->int_cap, sizeof(float) * total))) return rc;
+        CU(c, cudaMemcpyAsync(c->d_intensity, images, sizeof(float) * total, cudaMemcpyHostToDevice, s));
+        d_img = c->d_intensity;
+        if (photon_prob) {
+            if ((rc = ensure(c, (void**)&c->d_pprob, &c->pp_cap, sizeof(float) * total))) return rc;
+            CU(c, cudaMemcpyAsync(c->d_pprob, photon_prob, sizeof(float) * total, cudaMemcpyHostToDevice, s));
+            d_pp = c->d_pprob;
+        }
+    }
+    if (post_flags & DRR_POST_NOISE) {
+        if ((rc = ensure(c, (void**)&c->d_scratch, &c->scratch_cap, sizeof(float) * total))) return rc;
+        CU(c, drr_launch_noise(d_img, d_pp, c->d_scratch, W, H, n_views, photon_count, seed, s));
+        c->launches += 2;
+    }
+    if (post_flags & DRR_POST_CLIP) { CU(c, drr_launch_clip(d_img, total, intensity_upper_bound, s)); c->launches += 1; }
+    if (post_flags & DRR_POST_NEGLOG) {
+        if (c->minmax_cap < n_views) {
+            cudaFree(c->d_minmax); cudaFree(c->d_viewsum);
+            CU(c, cudaMalloc(&c->d_minmax, sizeof(unsigned) * 2 * n_views));
+            CU(c, cudaMalloc(&c->d_viewsum, sizeof(double) * n_views));
+            c->minmax_cap = n_views;
+        }
+        CU(c, drr_launch_neglog(d_img, npix, n_views, c->d_minmax, 0.01f, s));
+        c->launches += 2;
+    }
+    if (mem_kind == DRR_MEM_HOST) CU(c, cudaMemcpyAsync(images, d_img, sizeof(float) * total, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
     return DRR_OK;
 }
 

@@ -21,9 +21,18 @@
 
 #define TILE_W 8
 #define TILE_H 4
-#define SEG 32
-#define MAXC 256                       // cells staged per warp and segment
+#ifndef SEG_ALU
+#define SEG_ALU 32                     // steps per segment, ALU sampler
+#endif
+#ifndef SEG_TEX
+#define SEG_TEX 64                     // steps per segment, TEX sampler (stages label codes only)
+#endif
+#define MAXC 256                       // cells staged per warp and segment (ALU sampler: 32 B record + 1 B code each)
 #define WARP_SMEM (MAXC * 32 + MAXC)   // coefficient records + codes
+#define MAXC_TEX WARP_SMEM             // the TEX sampler uses the whole buffer for codes
+#ifndef MIN_BLOCKS
+#define MIN_BLOCKS 3
+#endif
 #define WARPS_PER_BLOCK 8
 
 // ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
@@ -108,7 +117,8 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
 
     while (t < t_end) {
         // ---- 1. bound the cells of this segment ------------------------------------------------
-        int S = min(SEG, t_end - t);
+        int S = min(USE_TEX ? SEG_TEX : SEG_ALU, t_end - t);
+        const int cap = USE_TEX ? MAXC_TEX : MAXC;
         int blx, bly, blz, nx, ny, nz;
         bool any;
         for (;;) {
@@ -126,7 +136,7 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
             any = bhx >= blx;
             if (!any) break;
             nx = bhx - blx + 1; ny = bhy - bly + 1; nz = bhz - blz + 1;
-            if (nx * ny * nz <= MAXC || S == 1) break;
+            if (nx * ny * nz <= cap || S == 1) break;
             S >>= 1;
         }
         if (!any) {  // nobody samples in this segment: just advance alpha
@@ -135,7 +145,7 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
             continue;
         }
         const int ncell = nx * ny * nz;
-        if (ncell > MAXC) {
+        if (ncell > cap) {
             // Even a single step of this tile does not fit the staging buffer (rays far apart compared with
             // the voxel size): take the generic per-sample path for this step.  Correct for any geometry;
             // the host picks the per-ray kernel for such set-ups (drr_capi.cu: pick_variant).
@@ -251,11 +261,12 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
 }
 
 template <int NM>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) march_warp_kernel(const __grid_constant__ MarchParams P) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_kernel(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
-    uint8_t* s_code = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
+    uint8_t* s_code_alu = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
+    uint8_t* s_code_tex = smem_raw + (size_t)warp * WARP_SMEM;
     const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
     const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
@@ -277,8 +288,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) march_warp_kernel(const 
         const bool tex_role = ((tile * 5u) & 7u) < (unsigned)P.tex_eighths;
         float acc[NM];
         const ViewDev& vw = P.views[view];
-        if (tex_role) march_tile<NM, true>(P, vw, udx, vdx, ok, s_coef, s_code, lane, acc, my_steps);
-        else march_tile<NM, false>(P, vw, udx, vdx, ok, s_coef, s_code, lane, acc, my_steps);
+        if (tex_role) march_tile<NM, true>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps);
+        else march_tile<NM, false>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps);
         if (ok) {
             float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
 #pragma unroll

@@ -125,8 +125,10 @@ class Projector(object):
             self.scatter_num = scatter_num
         if self.scatter_num > 0 and self.device is None:
             raise ValueError("Must provide device to simulate scatter.")
-        if self.scatter_num > 0:
-            raise DeprecationError("Scatter is deprecated.")
+        # The reference raises DeprecationError("Scatter is deprecated.") here (:530-531) because its transport kernel
+        # was removed; BASELINE.json's north_star asks for the kernel back, so scatter_num > 0 is functional again
+        # (deepdrr_b200/scatter.py, csrc/drr_scatter.cu).
+        self.scatter_seed = 0
 
         self.add_noise = add_noise
         self.photon_count = photon_count
@@ -224,6 +226,10 @@ class Projector(object):
                                               _lib.MEM_HOST, 0, ctypes.byref(vid)), h)
             self._mesh_state = None
             self._upload_meshes()
+            if self.scatter_num > 0:
+                from . import scatter as _scatter
+
+                _scatter.setup(self)
             sampler = {"alu": _lib.SAMPLER_ALU, "tex": _lib.SAMPLER_TEX, "hybrid": _lib.SAMPLER_HYBRID}[self.sampler]
             _lib.check(lib.drr_set_march(h, self.step, int(self.attenuate_outside_volume), int(self.air_index), sampler), h)
         except Exception:
@@ -300,9 +306,42 @@ class Projector(object):
         camera_projections = self._prepare_project(camera_projections)
         if max_ray_length is not None:
             self.max_ray_length = float(max_ray_length)
-        images = self._project_batch(camera_projections, want="intensity")
+        if self.scatter_num > 0:
+            images = self._project_with_scatter(camera_projections)
+        else:
+            images = self._project_batch(camera_projections, want="intensity")
         if images.shape[0] == 1:
             return images[0]
+        return images
+
+    def _project_with_scatter(self, camera_projections) -> np.ndarray:
+        """primary (ray march) + Monte Carlo scatter, then the usual noise / clip / neglog (reference :691-702)."""
+        from . import scatter as _scatter
+        from .parallel import shard_range
+
+        rank, world = 0, 1
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        images, pprob = self._project_batch(camera_projections, want="intensity+photon_prob")
+        n = int(self.scatter_num)
+        self.last_scatter_counters = []
+        for i, proj in enumerate(camera_projections):
+            a, b = shard_range(n, rank, world)  # photons shard over GPUs, the tally is all-reduced (NCCL)
+            tally, counters = _scatter.simulate(self, proj, b - a, seed=self.scatter_seed + i, photon_offset=a)
+            tally = _scatter.reduce_over_ranks(tally)
+            images[i] += _scatter.scatter_image(tally, n, proj)
+            self.last_scatter_counters.append(counters)
+        flags = (_lib.POST_NOISE if self.add_noise else 0) | (_lib.POST_CLIP if self.intensity_upper_bound is not None else 0) | \
+                (_lib.POST_NEGLOG if self.neglog else 0)
+        if flags:
+            H, W = images.shape[1:]
+            _lib.check(_lib.load().drr_postprocess(self._h, _lib.ptr(images), _lib.ptr(pprob), images.shape[0], W, H, flags, float(self.photon_count),
+                                                   float(self.intensity_upper_bound or 0.0), int(self.noise_seed or 0), _lib.MEM_HOST), self._h)
         return images
 
     def project_line_integrals(self, *camera_projections, max_ray_length: Optional[float] = None) -> np.ndarray:

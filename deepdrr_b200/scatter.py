@@ -1,0 +1,112 @@
+"""Monte Carlo scatter for the Projector (north_star kernel 3), host side.
+
+The reference rejects ``scatter_num > 0`` (projector.py:530-531) because its transport kernel was removed; what
+it still ships are the MC-GPU data tables (mcgpu_mfp_data.py, mcgpu_rita_samplers.py, mcgpu_compton_data.py,
+mcgpu_density.py) and the material-name mapping of conv_to_mcgpu.py:15-35.  Those tables are packed in
+``data/mcgpu_tables.npz`` (tools/gen_scatter_tables.py); the transport runs in libdrr_b200 (csrc/drr_scatter.cu).
+
+Photons shard over GPUs: rank r of w simulates the photon ids ``[r*n/w, (r+1)*n/w)`` of the same Philox stream and
+the integer tallies are summed with one NCCL all-reduce -- the sum is exact, so the result does not depend on w.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mcgpu_tables.npz")
+
+# deepdrr material name -> MC-GPU material (conv_to_mcgpu.py:15-35; the extra identities are table names)
+MCGPU_NAME = {"air": "air", "bone": "bone", "soft tissue": "soft tissue", "lung": "lung", "titanium": "titanium", "muscle": "muscle",
+              "blood": "blood", "water": "water", "adipose": "adipose", "PMMA": "PMMA"}
+
+_tables = None
+
+
+def load_tables():
+    global _tables
+    if _tables is None:
+        z = np.load(_DATA)
+        _tables = {k: z[k] for k in z.files}
+    return _tables
+
+
+def setup(projector) -> None:
+    """Upload the interaction tables for ``projector``'s materials (one volume only)."""
+    if len(projector.volumes) != 1:
+        raise ValueError("scatter simulation supports exactly one volume")
+    t = load_tables()
+    names = [str(n) for n in t["names"]]
+    mat_of_label = []
+    for m in projector.all_materials:
+        if m not in MCGPU_NAME or MCGPU_NAME[m] not in names:
+            raise ValueError(f"UNSUPPORTED MATERIAL FOR MCGPU: {m}")  # conv_to_mcgpu.py:24-33
+        mat_of_label.append(names.index(MCGPU_NAME[m]))
+    vol = projector.volumes[0]
+    from .scene import remap_labels
+
+    labels = remap_labels(vol, projector.all_materials)
+    rho_max = np.array([float(vol.data[labels == l].max()) if np.any(labels == l) else 0.0 for l in range(len(projector.all_materials))],
+                       dtype=np.float32)
+    e = t["energy_eV"].astype(np.float64)
+    mfp = np.ascontiguousarray(t["mfp_mm"], dtype=np.float32)
+    rita = np.ascontiguousarray(t["rita"], dtype=np.float32)
+    comp = np.ascontiguousarray(t["compton"], dtype=np.float32)
+    nshell = np.ascontiguousarray(t["nshell"], dtype=np.int32)
+    rho_nom = np.ascontiguousarray(t["density"], dtype=np.float32)
+    mol = np.ascontiguousarray(mat_of_label, dtype=np.int32)
+    _lib.check(_lib.load().drr_set_scatter_tables(projector._h, len(names), len(e), float(e[0]), float(e[1] - e[0]), _lib.ptr(mfp), _lib.ptr(rita),
+                                                  _lib.ptr(comp), _lib.ptr(nshell), _lib.ptr(rho_nom), _lib.ptr(mol), _lib.ptr(rho_max)), projector._h)
+
+
+def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int = 0, sdd: Optional[float] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Photons [photon_offset, photon_offset + n_photons) for one view -> (tally uint64 [H, W], counters float64 [8])."""
+    from . import geo
+
+    sdd = float(sdd if sdd is not None else projector.source_to_detector_distance)
+    if not sdd > 0:
+        raise ValueError("scatter needs the source-to-detector distance (pass a device)")
+    W, H = proj.intrinsic.sensor_size
+    w2i, _, ijk = geo.pose_arrays(proj, projector.volumes)
+    p_idx = np.ascontiguousarray(np.asarray(proj.index_from_world, dtype=np.float64)[:3, :] / sdd, dtype=np.float32)
+    src = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32)
+    tally = np.zeros((H, W), dtype=np.uint64)
+    counters = np.zeros(8, dtype=np.float64)
+    _lib.check(_lib.load().drr_scatter(projector._h, int(n_photons), int(photon_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, W, H, _lib.ptr(w2i),
+                                       _lib.ptr(p_idx), _lib.ptr(src), _lib.ptr(np.ascontiguousarray(ijk[0])), _lib.ptr(tally), _lib.ptr(counters),
+                                       _lib.MEM_HOST), projector._h)
+    return tally, counters
+
+
+def reduce_over_ranks(tally: np.ndarray) -> np.ndarray:
+    """Sum the integer tallies of all ranks (NCCL all-reduce on GPUs, gloo on CPU); identity without torch.distributed."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return tally
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tally
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(tally.view(np.int64).copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().view(np.uint64)
+
+
+def scatter_image(tally: np.ndarray, n_photons_total: int, proj) -> np.ndarray:
+    """Scatter signal in the units of the primary image: keV arriving in a pixel per photon emitted towards it.
+
+    Photons are emitted uniformly over the detector area with weight |r|^-3 (solid angle), r = world_from_index (u, v, 1);
+    the expected weighted number emitted towards pixel p is N / (W H) * |r_p|^-3.
+    """
+    H, W = tally.shape
+    m = np.asarray(proj.world_from_index, dtype=np.float64)[:3, :]
+    u, v = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    r = np.stack([u, v, np.ones_like(u)], axis=-1) @ m.T
+    wgt = np.linalg.norm(r, axis=-1) ** -3
+    emitted = n_photons_total / float(W * H) * wgt
+    return (tally.astype(np.float64) / 65536.0 / 1000.0 / emitted).astype(np.float32)

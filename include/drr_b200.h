@@ -120,6 +120,26 @@ int drr_set_mesh_poses(drr_ctx* ctx, int n_views, const float* world_from_mesh, 
  * lists of n (<= 128) slots (distance, facing: +1 entry / -1 exit / 0 empty) in place. */
 int drr_mesh_clean_hits(drr_ctx* ctx, float* ts, int8_t* facing, int n_rays, int n, float far_limit, int mem_kind);
 
+/* Monte Carlo scatter (north_star kernel 3).  The reference has no scatter kernel any more (projector.py:530-531
+ * raises); these entry points take its MC-GPU data tables (mcgpu_mfp_data.py, mcgpu_rita_samplers.py,
+ * mcgpu_compton_data.py, mcgpu_density.py) and one volume added with drr_add_volume.
+ *   mfp [n_mat][n_e][5] = Rayleigh, Compton, photoelectric, total mean free paths in mm at nominal density and the
+ *   Rayleigh max cumulative probability, on the energy grid e0 + i*de (eV); rita [n_mat][128][4] = x^2, P, A, B;
+ *   compton [n_mat][30][3] = shell electrons, ionisation energy (eV), J0; rho_nom [n_mat];
+ *   mat_of_label [M]: global material index -> table material; rho_max_of_label [M]: largest voxel density per label. */
+int drr_set_scatter_tables(drr_ctx* ctx, int n_mat, int n_e, float e0, float de, const float* mfp, const float* rita,
+                           const float* compton, const int* nshell, const float* rho_nom, const int* mat_of_label,
+                           const float* rho_max_of_label);
+/* Simulates photons [photon_offset, photon_offset + n_photons) of the stream `seed` for one view and returns the
+ * scatter tally: out_tally [H][W] uint64, energy x solid-angle weight in units of 2^-16 eV (exact integer sums, so
+ * any split of the photon range over calls or GPUs adds up bit-identically; reduce across GPUs with ncclAllReduce).
+ *   index_from_world: 3x4 K[R|t] divided by the source-to-detector distance (w == 1 on the detector plane).
+ *   out_counters (host, may be NULL): energy bookkeeping, eV x weight: emitted, missed the volume, absorbed, left
+ *   unscattered, scattered & detected, scattered & missed the detector; then #Rayleigh and #Compton events. */
+int drr_scatter(drr_ctx* ctx, unsigned long long n_photons, unsigned long long photon_offset, uint64_t seed, int W, int H,
+                const float* world_from_index, const float* index_from_world, const float* source_world,
+                const float* ijk_from_world, unsigned long long* out_tally, double* out_counters, int out_mem_kind);
+
 /* Replaces: the per-view loop of Projector.project -> _render_single (projector.py:679-685, 709-800):
  * _update_object_locations uploads (802-831), the projectKernel launch (770-774), the two D2H copies
  * and swapaxes (786-792) and the host post-processing (691-702), for a whole batch of views.
@@ -131,6 +151,11 @@ int drr_project(drr_ctx* ctx, int n_views, int W, int H, const float* world_from
                 const float* ijk_from_world, float max_ray_length, unsigned post_flags, float photon_count,
                 float intensity_upper_bound, float pixel_area_mm2, uint64_t seed, float* out_intensity,
                 float* out_photon_prob, float* out_area, int out_mem_kind);
+
+/* Replaces: the host post-processing of Projector.project (projector.py:691-702) for images that were
+ * modified after drr_project (e.g. primary + scatter): noise, clip, neglog on [n_views][H][W] in place. */
+int drr_postprocess(drr_ctx* ctx, float* images, const float* photon_prob, int n_views, int W, int H, unsigned post_flags,
+                    float photon_count, float intensity_upper_bound, uint64_t seed, int mem_kind);
 
 /* Kernel-only timing of the last drr_project (CUDA events on the handle's stream), ms:
  * [0] ray march, [1] spectral/post kernels, [2] whole call incl. copies. */

@@ -79,3 +79,34 @@ def test_two_rank_view_sharding_matches_single_rank(n_views):
     single = _OracleProjector().project(*_poses(n_views))
     assert gathered.shape == single.shape
     assert np.array_equal(gathered, single)
+
+
+def _tally_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepdrr_b200.scatter import reduce_over_ranks
+
+    rng = np.random.default_rng(100 + rank)
+    mine = rng.integers(0, 2**40, size=(6, 5), dtype=np.uint64)
+    total = reduce_over_ranks(mine)
+    q.put((rank, mine, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_tally_reduce_is_an_exact_integer_sum():
+    """The scatter tallies of all ranks are summed with one all-reduce (NCCL on GPUs, gloo here)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 17
+    procs = [ctx.Process(target=_tally_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    expect = got[0][1] + got[1][1]
+    assert np.array_equal(got[0][2], expect) and np.array_equal(got[1][2], expect)

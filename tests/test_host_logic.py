@@ -108,8 +108,8 @@ def test_projector_constructor_contract():
     class Dev:
         source_to_detector_distance = 1000.0
         camera_intrinsics = k
-    with pytest.raises(DeprecationError):
-        Projector(v, device=Dev(), scatter_num=100)                            # projector.py:530-531
+    # the reference raises DeprecationError here (projector.py:530-531); scatter is functional again in this build
+    assert Projector(v, device=Dev(), scatter_num=100).scatter_num == 100
 
 
 def test_initialize_fails_loudly_without_gpu():
