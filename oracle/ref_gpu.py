@@ -38,6 +38,7 @@ def _load():
                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_float)]
         lib.ref_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_set_mesh.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int]
         lib.ref_tide.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
         _lib = lib
     return _lib
@@ -56,10 +57,11 @@ class RefProjector:
     """One compiled (NUM_VOLUMES, NUM_MATERIALS) instance of the reference kernel."""
 
     def __init__(self, densities: Sequence[np.ndarray], labels_u8: Sequence[np.ndarray], num_materials: int,
-                 spacings: Optional[Sequence[Sequence[float]]] = None, device: int = 0, lineint: bool = False):
+                 spacings: Optional[Sequence[Sequence[float]]] = None, device: int = 0, lineint: bool = False, variant: str = ""):
+        """variant: "" (plain), "mesh" (MESH_ADDITIVE_ENABLED=1) or "att0" (ATTENUATE_OUTSIDE_VOLUME=1, AIR_INDEX=0)."""
         lib = _load()
         V = len(densities)
-        kind = "lineint" if lineint else "project"
+        kind = ("lineint" if lineint else "project") + (("_" + variant) if variant else "")
         path = os.path.join(_REF, f"ref_{kind}_V{V}_M{num_materials}.cubin")
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path}: add the (V, M) pair to oracle/Makefile CONFIGS and rebuild")
@@ -72,6 +74,16 @@ class RefProjector:
             sp = (1.0, 1.0, 1.0) if spacings is None else spacings[v]
             _chk(lib.ref_add_volume(self.h, _p(d), _p(l), d.shape[0], d.shape[1], d.shape[2], sp[0], sp[1], sp[2]))
         self._spectrum = None
+
+    def set_mesh(self, mesh: dict, npix: int):
+        """Feed the mesh buffers projectKernel consumes (same dict as oracle.cpu_oracle.project(mesh=...))."""
+        ha = np.ascontiguousarray(mesh["hit_alphas"], dtype=np.float32)
+        hf = np.ascontiguousarray(mesh["hit_facing"], dtype=np.int8)
+        lv = np.ascontiguousarray(mesh["layer_valid"], dtype=np.int8)
+        ad = np.ascontiguousarray(mesh["additive"], dtype=np.float32)
+        mm = np.ascontiguousarray(mesh["mesh_mats"], dtype=np.int32)
+        assert ha.shape[0] == 2 and ha.shape[2] == 32, "the cubins are compiled with MESH_LAYERS=2, MAX_MESH_HITS=32"
+        _chk(_load().ref_set_mesh(self.h, _p(ha), _p(hf), _p(lv), _p(ad), _p(mm), mm.size, npix))
 
     def set_spectrum(self, energies: np.ndarray, pdf: np.ndarray, mu: np.ndarray):
         e = np.ascontiguousarray(energies, dtype=np.float32)

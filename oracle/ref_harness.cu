@@ -46,6 +46,7 @@ struct RefHarness {
     int8_t *d_hit_facing = nullptr, *d_layer_valid = nullptr;
     float *d_additive = nullptr;
     int *d_mesh_mats = nullptr;
+    int n_mesh_mats = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
 };
@@ -171,6 +172,26 @@ int ref_add_volume(void* hp, const float* density, const uint8_t* labels, int ni
     return 0;
 }
 
+// Mesh inputs of projectKernel (project_kernel.cu:172-177) from host arrays laid out as the reference keeps them:
+// hit_alphas / hit_facing [layers][npix][max_hits], layer_valid [layers], additive [layers][n_mats][npix][2].
+int ref_set_mesh(void* hp, const float* hit_alphas, const int8_t* hit_facing, const int8_t* layer_valid, const float* additive,
+                 const int* mesh_mats, int n_mesh_mats, int npix) {
+    RefHarness* h = (RefHarness*)hp;
+    size_t nh = (size_t)h->mesh_layers * npix * h->max_mesh_hits, na = (size_t)h->mesh_layers * n_mesh_mats * npix * 2;
+    cudaFree(h->d_hit_alpha); cudaFree(h->d_hit_facing); cudaFree(h->d_additive); cudaFree(h->d_mesh_mats);
+    RH_CHECK(cudaMalloc(&h->d_hit_alpha, nh * 4 + 16));
+    RH_CHECK(cudaMalloc(&h->d_hit_facing, nh + 16));
+    RH_CHECK(cudaMalloc(&h->d_additive, na * 4 + 16));
+    RH_CHECK(cudaMalloc(&h->d_mesh_mats, n_mesh_mats * 4 + 16));
+    RH_CHECK(cudaMemcpy(h->d_hit_alpha, hit_alphas, nh * 4, cudaMemcpyHostToDevice));
+    RH_CHECK(cudaMemcpy(h->d_hit_facing, hit_facing, nh, cudaMemcpyHostToDevice));
+    RH_CHECK(cudaMemcpy(h->d_layer_valid, layer_valid, h->mesh_layers, cudaMemcpyHostToDevice));
+    RH_CHECK(cudaMemcpy(h->d_additive, additive, na * 4, cudaMemcpyHostToDevice));
+    RH_CHECK(cudaMemcpy(h->d_mesh_mats, mesh_mats, n_mesh_mats * 4, cudaMemcpyHostToDevice));
+    h->n_mesh_mats = n_mesh_mats;
+    return 0;
+}
+
 int ref_set_spectrum(void* hp, int n_bins, const float* energies, const float* pdf, const float* mu) {
     RefHarness* h = (RefHarness*)hp;
     if (h->d_energies) { cudaFree(h->d_energies); cudaFree(h->d_pdf); cudaFree(h->d_mu); }
@@ -211,7 +232,7 @@ int ref_project(void* hp, int W, int H, float step, const int* priority, const i
     RH_CHECK(cudaMemcpy(h->d_enabled, enabled, 4 * V, cudaMemcpyHostToDevice));
 
     void* solid = nullptr;
-    int n_mesh_mats = 0, off = 0;
+    int n_mesh_mats = h->n_mesh_mats, off = 0;
     void* args[] = {&h->d_vol_tex, &h->d_seg_tex, &W, &H, &step, &h->d_priority, &h->d_enabled,
                     &h->d_min[0], &h->d_min[1], &h->d_min[2], &h->d_max[0], &h->d_max[1], &h->d_max[2],
                     &h->d_vox[0], &h->d_vox[1], &h->d_vox[2], &h->d_src[0], &h->d_src[1], &h->d_src[2],

@@ -167,6 +167,50 @@ def test_ct_plus_meshes_matches_oracle():
 
 
 @pytest.mark.gpu
+def test_march_consumes_mesh_buffers_like_the_reference_kernel():
+    """The same hit lists / additive buffers fed to the reference's projectKernel (MESH_ADDITIVE_ENABLED=1 cubin) and to
+    the general march kernel through drr_set_mesh_buffers: line integrals must agree to 1e-5 everywhere."""
+    import ctypes
+    import torch
+    from deepdrr_b200 import _lib
+    from deepdrr_b200.scene import remap_labels
+    from oracle import ref_gpu
+
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not shipped")
+    ct, meshes = _scene()
+    carm = phantoms.MobileCArmGeometry(sensor_width=64, sensor_height=48, pixel_size=4.5)
+    pose = phantoms.c2_poses(1, seed=8, carm=carm)[0]
+    W, H = 64, 48
+    mats = ["air", "bone", "lung", "soft tissue", "titanium"]
+    labels = remap_labels(ct, mats)
+    w2i, src, ijk = geo.pose_arrays(pose, [ct])
+    mesh_mats = sorted({mats.index(m.material) for m in meshes})
+    mb = mesh_oracle.mesh_buffers(_prims_for_oracle(meshes, mats), w2i, pose.center_in_world, W, H, 2, 32, 2 * carm.source_to_detector_distance, mesh_mats)
+    ref = ref_gpu.RefProjector([ct.data], [labels], 5, lineint=True, variant="mesh")
+    ref.set_mesh(mb, W * H)
+    li = ref.line_integrals(W, H, 0.25, w2i, src, ijk, carm.max_ray_length)
+    ref.close()
+    # same buffers into the B200 library
+    with Projector([ct], spectrum="90KV_AL40", neglog=False, step=0.25, camera_intrinsics=carm.camera_intrinsics) as p:
+        p.all_materials = mats  # the material universe of the full scene
+    with Projector([ct] + [mm for mm in meshes], spectrum="90KV_AL40", neglog=False, step=0.25, camera_intrinsics=carm.camera_intrinsics,
+                   source_to_detector_distance=carm.source_to_detector_distance) as p:
+        lib, h = _lib.load(), p._h
+        _lib.check(lib.drr_set_meshes(h, 0, None, None, None, None, None, None, 2, 32), h)       # drop the library's own tracing
+        p.meshes = []
+        dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in mb.items()}
+        _lib.check(lib.drr_set_mesh_buffers(h, 2, 32, dev["hit_alphas"].data_ptr(), dev["hit_facing"].data_ptr(), dev["layer_valid"].data_ptr(),
+                                            dev["additive"].data_ptr(), dev["mesh_mats"].data_ptr(), len(mesh_mats), _lib.MEM_DEVICE), h)
+        area = p.project_arrays(w2i[None], src[None], ijk[None], (W, H), carm.max_ray_length, want="area")[0]
+    for m in range(5):
+        mask = li[m] > 0
+        assert np.all(area[m][~mask] == 0)
+        if mask.any():
+            assert cases.rel_err(area[m], li[m])[mask].max() <= 1e-5, mats[m]
+
+
+@pytest.mark.gpu
 def test_mesh_only_sphere_chord_and_enable_toggle():
     v, f = phantoms.icosphere(30.0, 3)
     ball = Mesh(v, f, material="iron", density=2.0)
