@@ -6,6 +6,6 @@ volume / material / spectrum data contracts it consumes, and the CUDA library be
 from . import geo, vol
 from .material import Material
 from .projector import DeprecationError, Projector
-from .vol import Volume
+from .vol import HUVolume, Mesh, Volume
 
-__all__ = ["Projector", "Volume", "Material", "geo", "vol", "DeprecationError"]
+__all__ = ["Projector", "Volume", "HUVolume", "Mesh", "Material", "geo", "vol", "DeprecationError"]

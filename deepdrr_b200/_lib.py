@@ -24,7 +24,7 @@ MAX_VOLUMES, MAX_MATERIALS = 8, 16
 
 # every symbol include/drr_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
-    "drr_create", "drr_destroy", "drr_last_error", "drr_set_stream", "drr_set_spectrum", "drr_add_volume",
+    "drr_create", "drr_destroy", "drr_last_error", "drr_set_stream", "drr_set_spectrum", "drr_add_volume", "drr_add_volume_hu",
     "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_tuning", "drr_set_mesh_buffers", "drr_set_meshes", "drr_set_mesh_poses", "drr_mesh_clean_hits", "drr_set_scatter_tables", "drr_scatter", "drr_postprocess",
     "drr_project", "drr_last_timing", "drr_last_sample_count", "drr_launch_count", "drr_synchronize", "drr_version",
 ]
@@ -54,6 +54,7 @@ def load() -> ctypes.CDLL:
     lib.drr_set_stream.argtypes = [vp, vp]
     lib.drr_set_spectrum.argtypes = [vp, ci, ci, vp, vp, vp]
     lib.drr_add_volume.argtypes = [vp, vp, vp, ci, ci, ci, ci, cu, ctypes.POINTER(ci)]
+    lib.drr_add_volume_hu.argtypes = [vp, vp, ci, ci, ci, ci, vp, cu, ctypes.POINTER(ci)]
     lib.drr_clear_volumes.argtypes = [vp]
     lib.drr_set_priorities.argtypes = [vp, vp, vp, ci]
     lib.drr_set_march.argtypes = [vp, cf, ci, ci, ci]

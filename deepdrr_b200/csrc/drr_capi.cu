@@ -95,6 +95,22 @@ __global__ void transpose_ik_kernel(const T* __restrict__ in, T* __restrict__ ou
     }
 }
 
+// HU -> (density, label) on the device.  Same float32 arithmetic as the host path:
+// density = max(min(0.001029*HU + 1.03, 0.0005886*HU + 1.03), 0) (vol/volume.py:338-351), labels by the thresholds of
+// load_dicom.py:132-143 packed like _format_materials (vol/volume.py:955-992), then remapped to the global index.
+__global__ void hu_prepare_kernel(const float* __restrict__ hu, size_t n, int l_air, int l_soft, int l_bone, float* __restrict__ dens,
+                                  uint8_t* __restrict__ lab) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float h = hu[i];
+    const float a = __fadd_rn(__fmul_rn(0.001029f, h), 1.030f), b = __fadd_rn(__fmul_rn(0.0005886f, h), 1.03f);
+    dens[i] = fmaxf(fminf(a, b), 0.0f);
+    int l = l_air;                        // unlabeled voxels (NaN) stay at id 0 = the first material, air
+    if (-800.0f < h && h <= 350.0f) l = l_soft;
+    if (350.0f < h) l = l_bone;
+    lab[i] = (uint8_t)l;
+}
+
 // One thread per cell base (bi, bj, bk) in [-2, n-2]^3: gathers the 8 clamped corner texels / labels
 // and stores the filter-coefficient record (see hw_trilinear_cell) and the label record.
 __global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t* __restrict__ lab, int ni, int nj, int nk,
@@ -328,10 +344,10 @@ int drr_set_spectrum(drr_ctx* c, int n_bins, int M, const float* energies, const
     return DRR_OK;
 }
 
-int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind, unsigned flags,
-                   int* vol_id) {
+static int add_volume_impl(drr_ctx* c, const float* density, const uint8_t* labels, const float* hu, const int* hu_labels, int ni, int nj, int nk,
+                           int mem_kind, unsigned flags, int* vol_id) {
     if (!c) return DRR_E_INVALID;
-    if (!density || !labels || ni <= 0 || nj <= 0 || nk <= 0) return fail(c, DRR_E_INVALID, "drr_add_volume: bad arguments");
+    if ((!hu && (!density || !labels)) || ni <= 0 || nj <= 0 || nk <= 0) return fail(c, DRR_E_INVALID, "drr_add_volume: bad arguments");
     if ((int)c->vols.size() >= DRR_MAX_VOLUMES) return fail(c, DRR_E_INVALID, "drr_add_volume: at most %d volumes", DRR_MAX_VOLUMES);
     if (ni > 16384 || nj > 16384 || nk > 16384) return fail(c, DRR_E_INVALID, "drr_add_volume: dimension above 16384");
     CU(c, cudaSetDevice(c->device));
@@ -341,7 +357,9 @@ int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int 
     v.ni = ni; v.nj = nj; v.nk = nk;
     float* d_in = nullptr;
     uint8_t* l_in = nullptr;
-    auto cleanup = [&]() { free_volume(v); if (mem_kind == DRR_MEM_HOST) { cudaFree(d_in); cudaFree(l_in); } };
+    float* hu_dev = nullptr;
+    const bool own_in = (mem_kind == DRR_MEM_HOST) || hu;
+    auto cleanup = [&]() { free_volume(v); if (own_in) { cudaFree(d_in); cudaFree(l_in); } if (hu && mem_kind == DRR_MEM_HOST) cudaFree(hu_dev); };
 #define CUV(x)                                                                                                     \
     do {                                                                                                           \
         cudaError_t e_ = (x);                                                                                      \
@@ -350,7 +368,18 @@ int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int 
             return fail(c, e_ == cudaErrorMemoryAllocation ? DRR_E_NOMEM : DRR_E_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
         }                                                                                                          \
     } while (0)
-    if (mem_kind == DRR_MEM_HOST) {
+    if (hu) {
+        CUV(cudaMalloc(&d_in, n * sizeof(float)));
+        CUV(cudaMalloc(&l_in, n));
+        hu_dev = const_cast<float*>(hu);
+        if (mem_kind == DRR_MEM_HOST) {
+            CUV(cudaMalloc(&hu_dev, n * sizeof(float)));
+            CUV(cudaMemcpyAsync(hu_dev, hu, n * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+        hu_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hu_dev, n, hu_labels[0], hu_labels[1], hu_labels[2], d_in, l_in);
+        c->launches += 1;
+        CUV(cudaGetLastError());
+    } else if (mem_kind == DRR_MEM_HOST) {
         CUV(cudaMalloc(&d_in, n * sizeof(float)));
         CUV(cudaMalloc(&l_in, n));
         CUV(cudaMemcpyAsync(d_in, density, n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -396,11 +425,27 @@ int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int 
         CUV(cudaCreateTextureObject(&v.tex, &rd, &td, nullptr));
     }
     CUV(cudaStreamSynchronize(s));
-    if (mem_kind == DRR_MEM_HOST) { cudaFree(d_in); cudaFree(l_in); }
+    if (own_in) { cudaFree(d_in); cudaFree(l_in); }
+    if (hu && mem_kind == DRR_MEM_HOST) cudaFree(hu_dev);
 #undef CUV
     c->vols.push_back(v);
     if (vol_id) *vol_id = (int)c->vols.size() - 1;
     return DRR_OK;
+}
+
+int drr_add_volume(drr_ctx* c, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind, unsigned flags,
+                   int* vol_id) {
+    return add_volume_impl(c, density, labels, nullptr, nullptr, ni, nj, nk, mem_kind, flags, vol_id);
+}
+
+int drr_add_volume_hu(drr_ctx* c, const float* hu, int ni, int nj, int nk, int mem_kind, const int* labels_air_soft_bone, unsigned flags,
+                      int* vol_id) {
+    if (!c) return DRR_E_INVALID;
+    if (!hu || !labels_air_soft_bone) return fail(c, DRR_E_INVALID, "drr_add_volume_hu: bad arguments");
+    for (int k = 0; k < 3; k++)
+        if (labels_air_soft_bone[k] < 0 || labels_air_soft_bone[k] >= DRR_MAX_MATERIALS)
+            return fail(c, DRR_E_INVALID, "drr_add_volume_hu: material index out of range");
+    return add_volume_impl(c, nullptr, nullptr, hu, labels_air_soft_bone, ni, nj, nk, mem_kind, flags, vol_id);
 }
 
 int drr_set_priorities(drr_ctx* c, const int* priority, const int* enabled, int n) {

@@ -219,6 +219,12 @@ class Projector(object):
             _lib.check(lib.drr_set_spectrum(h, len(energies), len(self.all_materials), _lib.ptr(energies), _lib.ptr(pdf),
                                             _lib.ptr(mu)), h)
             for _vol in self.volumes:
+                if isinstance(_vol, vol.HUVolume):  # HU -> density + segmentation on the device
+                    cls = np.array([self.all_materials.index(k) for k in ("air", "soft tissue", "bone")], dtype=np.int32)
+                    vid = ctypes.c_int(-1)
+                    _lib.check(lib.drr_add_volume_hu(h, _lib.ptr(_vol.hu), _vol.hu.shape[0], _vol.hu.shape[1], _vol.hu.shape[2], _lib.MEM_HOST,
+                                                     _lib.ptr(cls), 0, ctypes.byref(vid)), h)
+                    continue
                 dens = np.ascontiguousarray(np.asarray(_vol.data), dtype=np.float32)
                 labels = np.ascontiguousarray(remap_labels(_vol, self.all_materials))
                 vid = ctypes.c_int(-1)

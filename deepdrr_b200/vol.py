@@ -141,6 +141,54 @@ class Volume(Renderable):
         return self.anatomical_from_IJK @ (np.array(self.shape, dtype=np.float64) / 2)
 
 
+class HUVolume(Volume):
+    """A CT given in Hounsfield units whose density / threshold segmentation are computed on the GPU at
+    ``Projector.initialize``; the host arrays are only built if somebody asks for them.
+
+    Equivalent to ``Volume.from_hu(hu, ...)`` -- same materials (air, soft tissue, bone), same float32 arithmetic.
+    """
+
+    def __init__(self, hu_values: np.ndarray, anatomical_from_IJK=None, world_from_anatomical=None, enabled: bool = True, **kwargs):
+        Renderable.__init__(self, anatomical_from_IJK, world_from_anatomical, enabled=enabled, **kwargs)
+        assert np.ndim(hu_values) == 3, "Volume data must be 3D."
+        self.hu = np.ascontiguousarray(hu_values, dtype=np.float32)
+        self.anatomical_coordinate_system = None
+        self._host = None
+
+    def _materialise(self):
+        if self._host is None:
+            self._host = (convert_hounsfield_to_density(self.hu).astype(np.float32), format_materials(segment_materials_thresholding(self.hu)))
+        return self._host
+
+    @property
+    def data(self):
+        return self._materialise()[0]
+
+    @property
+    def materials(self):
+        if self._host is None:  # the name -> id map is known without touching the voxels
+            return {"air": 0, "soft tissue": 1, "bone": 2}, _LazyLabels(self)
+        return self._host[1]
+
+    @property
+    def shape(self):
+        return self.hu.shape
+
+
+class _LazyLabels:
+    """Stands in for the uint16 label array of an HUVolume until it is really needed."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._owner._materialise()[1][1]
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, k):
+        return self._owner._materialise()[1][1][k]
+
+
 # Default mesh densities in g/cm^3 by material name (reference: pyrenderdrr/material.py:5-20).
 DEFAULT_MESH_DENSITIES = {
     "bone": 1.92, "soft tissue": 1.0, "tissue_soft": 1.0, "blood": 1.06, "muscle": 1.06, "air": 0.0012, "iron": 7.87,

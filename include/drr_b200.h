@@ -74,6 +74,11 @@ int drr_set_spectrum(drr_ctx* ctx, int n_bins, int n_materials, const float* ene
  * flags: bit0 = skip cell records (TEX-only handle), bit1 = skip texture (ALU-only handle). */
 int drr_add_volume(drr_ctx* ctx, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind,
                    unsigned flags, int* vol_id);
+/* Same, from a Hounsfield-unit volume: HU -> density (vol/volume.py:338-351) and threshold segmentation
+ * air <= -800 < soft tissue <= 350 < bone (load_dicom.py:132-143, vol/volume.py:955-992) run on the device, so the
+ * host never materialises density / label arrays.  labels_air_soft_bone = global material indices of the three classes. */
+int drr_add_volume_hu(drr_ctx* ctx, const float* hu, int ni, int nj, int nk, int mem_kind, const int* labels_air_soft_bone,
+                      unsigned flags, int* vol_id);
 /* Drop all volumes (keeps spectrum).  Replaces the texture teardown in Projector.free. */
 int drr_clear_volumes(drr_ctx* ctx);
 

@@ -306,3 +306,23 @@ def test_outside_air_attenuation_vs_live_reference_kernel():
                 if mask.any():
                     assert cases.rel_err(area[n, m], li[m])[mask].max() <= LINE_RTOL
         ref.close()
+
+
+def test_gpu_side_hu_preparation_is_bit_identical_to_the_host_path():
+    """drr_add_volume_hu (HU -> density + threshold labels on the device) vs Volume.from_hu on the host."""
+    from deepdrr_b200 import HUVolume, Volume
+
+    hu = phantoms.thorax_hu((40, 48, 36), (10.0, 8.5, 11.0), seed=5)
+    hu[3, 4, 5] = np.nan                                                            # unlabeled voxel -> id 0 (air), density NaN-propagating max
+    hu[0, 0, 0], hu[1, 1, 1], hu[2, 2, 2] = -800.0, 350.0, 350.00003               # threshold edges
+    hu[3, 4, 5] = -800.00006
+    host = Volume.from_hu(hu, anatomical_from_IJK=geo.FrameTransform.from_scaling(8.0, (-160, -190, -150)))
+    dev_ = HUVolume(hu, anatomical_from_IJK=geo.FrameTransform.from_scaling(8.0, (-160, -190, -150)))
+    carm = phantoms.MobileCArmGeometry(sensor_width=64, sensor_height=48, pixel_size=4.5)
+    poses = phantoms.c2_poses(2, seed=31, carm=carm)
+    out = []
+    for v in (host, dev_):
+        with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=carm.camera_intrinsics, step=0.5) as p:
+            out.append(p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length))
+    assert dev_._host is None
+    assert np.array_equal(out[0], out[1])

@@ -133,3 +133,42 @@ def test_shard_ranges_cover_everything_once():
             assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def test_devices_follow_reference_geometry():
+    from deepdrr_b200 import device
+
+    c = device.MobileCArm(alpha=10, beta=-20, isocenter=(5, 6, 7))
+    g = phantoms.MobileCArmGeometry().camera_projection(np.radians(10), np.radians(-20), (5, 6, 7))
+    assert np.allclose(c.get_camera_projection().camera3d_from_world.data, g.camera3d_from_world.data, atol=1e-12)
+    assert c.camera_intrinsics.sensor_size == (1536, 1536) and abs(c.detector_width - 297.984) < 1e-9
+    c.move_by(delta_alpha=500)                                   # clipped to max_alpha (mobile_carm.py:295-303)
+    assert abs(np.degrees(c.alpha) - 110) < 1e-9
+    c.move_to(alpha=0, beta=0, isocenter_in_world=(1, 2, 3))
+    assert np.allclose(c.isocenter, (1, 2, 3)) and np.allclose(c.source_in_world, (1, 2, 3 - 530.0))
+    batch = c.camera_projections([10, 20], [-20, 5], np.array([[5, 6, 7], [0, 0, 0]]))
+    assert np.allclose(batch[0].camera3d_from_world.data, g.camera3d_from_world.data, atol=1e-12)
+    with pytest.raises(ValueError):
+        device.MobileCArm(isocenter=(1000, 0, 0), enforce_isocenter_bounds=True)
+
+    s = device.SimpleDevice(sensor_height=64, sensor_width=80, pixel_size=2.0)
+    s.set_view([10, 20, 30], [0.3, 1.0, 0.2], [0, 0, 1])
+    p = s.get_camera_projection()
+    d = p.world_from_index[:3] @ np.array([40, 32, 1.0])
+    d /= np.linalg.norm(d)
+    assert np.allclose(d, np.array([0.3, 1, 0.2]) / np.linalg.norm([0.3, 1, 0.2]), atol=1e-9)
+    assert np.allclose(p.center_in_world + 500 * d, [10, 20, 30], atol=1e-9)       # the point is mid-way (fraction 0.5)
+    up_cam = p.camera3d_from_world.R @ np.array([0, 0, 1.0])
+    assert up_cam[1] < -0.9 and abs(up_cam[0]) < 1e-9                              # world up shows as -y (image up)
+    assert s.camera_intrinsics.sensor_size == (80, 64) and s.camera_intrinsics.fx == 500.0
+
+
+def test_hu_volume_is_lazy_and_equivalent_on_the_host():
+    from deepdrr_b200 import HUVolume
+
+    hu = phantoms.c1_hu(12)
+    a, b = HUVolume(hu), Volume.from_hu(hu)
+    assert a.materials[0] == b.materials[0] and a._host is None and a.shape == b.shape
+    assert Projector(a, camera_intrinsics=geo.CameraIntrinsicTransform.from_sizes((8, 8), 1.0, 100.0)).all_materials == ["air", "bone", "soft tissue"]
+    assert a._host is None                                                          # nothing materialised so far
+    assert np.array_equal(a.data, b.data) and np.array_equal(np.asarray(a.materials[1]), b.materials[1])
