@@ -69,9 +69,13 @@ __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float 
     for (int m = 0; m < NM; m++) acc[m] = __fmaf_rn(wr, seg[m], acc[m]);
 }
 
-template <int NM, bool USE_TEX>
+// KTEX = how many samples of every group of 8 consecutive steps are fetched by the texture unit; the others are
+// interpolated on the FMA pipes from the staged cell records.  8 = TEX only (no records staged), 0 = ALU only.
+template <int NM, int KTEX>
 __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
                                            uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps) {
+    constexpr bool USE_TEX = KTEX > 0;      // general / slow samples go through the texture unit when there is one
+    constexpr bool STAGE_COEF = KTEX < 8;
     const VolDev& vol = P.vol[0];
     const float step = P.step;
 #pragma unroll
@@ -117,8 +121,8 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
 
     while (t < t_end) {
         // ---- 1. bound the cells of this segment ------------------------------------------------
-        int S = min(USE_TEX ? SEG_TEX : SEG_ALU, t_end - t);
-        const int cap = USE_TEX ? MAXC_TEX : MAXC;
+        int S = min(STAGE_COEF ? SEG_ALU : SEG_TEX, t_end - t);
+        const int cap = STAGE_COEF ? MAXC : MAXC_TEX;
         int blx, bly, blz, nx, ny, nz;
         bool any;
         for (;;) {
@@ -177,7 +181,7 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
                 s_code[e] = (uint8_t)cc;
                 same = same && (first_code < 0 || cc == first_code);
                 first_code = cc;
-                if (!USE_TEX) {  // slices interleaved for the packed f32x2 form (hw_trilinear_cell2)
+                if (STAGE_COEF) {  // slices interleaved for the packed f32x2 form (hw_trilinear_cell2)
                     const float4 c0 = __ldg(vol.cellc + 2 * cell), c1 = __ldg(vol.cellc + 2 * cell + 1);
                     s_coef[2 * e] = make_float4(c0.x, c1.x, c0.y, c1.y);
                     s_coef[2 * e + 1] = make_float4(c0.z, c1.z, c0.w, c1.w);
@@ -203,23 +207,50 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
                 cur = w_checkout<NM>(code0, live, acc);
             }
             const int t_stop = t + S;
-            if (USE_TEX) {
+            auto tex_sample = [&](float a) {
+                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                return tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
+            };
+            auto alu_sample = [&](float a) {
+                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
+                const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                return hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB);
+            };
+            if (KTEX == 8) {
 #pragma unroll 4
                 for (; t < t_stop; t++) {
-                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
-                    cur = __fadd_rn(cur, tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f)));  // K.cu:542
+                    cur = __fadd_rn(cur, tex_sample(alpha));
                     alpha = __fadd_rn(alpha, step);  // K.cu:552
                 }
-            } else {
+            } else if (KTEX == 0) {
 #pragma unroll 2
                 for (; t < t_stop; t++) {
-                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
-                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
-                    const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
-                    const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
-                    cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
-                    alpha = __fadd_rn(alpha, step);  // K.cu:552
+                    cur = __fadd_rn(cur, alu_sample(alpha));
+                    alpha = __fadd_rn(alpha, step);
+                }
+            } else {
+                // groups of 8 steps: the texture fetches are issued first, the FMA-pipe samples are computed while
+                // they are in flight, and the running total receives the eight values in step order (K.cu:544-546)
+                for (; t + 8 <= t_stop; t += 8) {
+                    float a[8], r[8];
+                    a[0] = alpha;
+#pragma unroll
+                    for (int j = 1; j < 8; j++) a[j] = __fadd_rn(a[j - 1], step);
+                    // which steps of the group use the texture unit: spread evenly (Bresenham)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 != (j * KTEX) / 8) r[j] = tex_sample(a[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 == (j * KTEX) / 8) r[j] = alu_sample(a[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) cur = __fadd_rn(cur, r[j]);
+                    alpha = __fadd_rn(a[7], step);
+                }
+                for (; t < t_stop; t++) {
+                    cur = __fadd_rn(cur, tex_sample(alpha));
+                    alpha = __fadd_rn(alpha, step);
                 }
             }
             continue;
@@ -246,7 +277,7 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
                 if (code != 0xFF) {
                     if (USE_TEX) {
                         cur = __fadd_rn(cur, rho);
-                    } else {
+                    } else if (STAGE_COEF) {
                         const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
                         cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
                     }
@@ -283,13 +314,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
         const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
         const bool ok = udx < P.W && vdx < P.H;
-        // The sampler is a function of the tile, not of the warp that happens to pull it, so results do
-        // not depend on scheduling; consecutive tiles alternate so every SM runs both kinds at once.
-        const bool tex_role = ((tile * 5u) & 7u) < (unsigned)P.tex_eighths;
+        // every tile uses the same sampler mix, and the mix is a function of the step index only, so results do not
+        // depend on scheduling
         float acc[NM];
         const ViewDev& vw = P.views[view];
-        if (tex_role) march_tile<NM, true>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps);
-        else march_tile<NM, false>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps);
+        switch (P.tex_eighths) {
+            case 0: march_tile<NM, 0>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            case 1: case 2: case 3:
+            case 4: march_tile<NM, 4>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            case 5: march_tile<NM, 5>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            case 6: march_tile<NM, 6>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            case 7: march_tile<NM, 7>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            default: march_tile<NM, 8>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps); break;
+        }
         if (ok) {
             float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
 #pragma unroll

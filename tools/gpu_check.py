@@ -25,15 +25,10 @@ def check(name, volumes, spectrum, priorities=None, samplers=("alu", "tex", "hyb
                        camera_intrinsics=geo.CameraIntrinsicTransform.from_sizes((W, H), 1.0, 1000.0), sampler=sampler) as p:
             i = 0
             while f"w2i_{i}" in g:
-                # feed the golden's exact matrices
-                p._pose_arrays = lambda cps, i=i: (g[f"w2i_{i}"].reshape(1, 9), g[f"src_{i}"].reshape(1, -1, 3), g[f"ijk_{i}"].reshape(1, -1, 12))
-                p.initialized = True
-                p.max_ray_length = float(g["max_ray_length"])
-                cp = [FixedProj(None, None, None, W, H)]
-                t = time.time()
-                area = p._project_batch(cp, want="area")[0]
+                arrs = (g[f"w2i_{i}"].reshape(1, 9), g[f"src_{i}"].reshape(1, -1, 3), g[f"ijk_{i}"].reshape(1, -1, 12))
+                area = p.project_arrays(*arrs, (W, H), float(g["max_ray_length"]), want="area")[0]
                 tm = p.last_timing_ms()
-                img = p._project_batch(cp, want="intensity")[0]
+                img = p.project_arrays(*arrs, (W, H), float(g["max_ray_length"]), want="intensity", raw=True)[0]
                 gl, gi = g[f"lineint_{i}"], g[f"intensity_{i}"]
                 a = area[:, ::sub, ::sub]; im = img[::sub, ::sub]
                 msg = f"{name} v{i} {sampler:6s} march {tm['march']:.2f} ms S={p.last_sample_count():.3e} I rel {rel(im, gi).max():.2e} |"
