@@ -135,11 +135,16 @@ __global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t
             }
     const size_t cell = ((size_t)ck * (nj + 1) + cj) * (ni + 1) + ci;
     const float s = 1.0f / 256.0f;
+    // per z-slice c: (T01, T10 - T01, T00 - T01, T11 - T10) / 256; the two slices are stored interleaved,
+    // A = (c0.x, c1.x, c0.y, c1.y), B = (c0.z, c1.z, c0.w, c1.w), which is the operand order of the f32x2 form
+    float4 cs[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         float t01 = T[c][0][1], t10 = T[c][1][0], t00 = T[c][0][0], t11 = T[c][1][1];
-        cellc[2 * cell + c] = make_float4(t01 * s, (t10 - t01) * s, (t00 - t01) * s, (t11 - t10) * s);
+        cs[c] = make_float4(t01 * s, (t10 - t01) * s, (t00 - t01) * s, (t11 - t10) * s);
     }
+    cellc[2 * cell] = make_float4(cs[0].x, cs[1].x, cs[0].y, cs[1].y);
+    cellc[2 * cell + 1] = make_float4(cs[0].z, cs[1].z, cs[0].w, cs[1].w);
     celll[cell] = make_uint2(lx, ly);
     const unsigned l0 = lx & 0xFF;
     const bool uniform = (lx == ly) && (lx == l0 * 0x01010101u);

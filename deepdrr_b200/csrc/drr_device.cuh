@@ -18,7 +18,7 @@
 struct VolDev {
     const float* dens;    // [nk][nj][ni] density, i fastest (texture order, projector.py:1468-1470)
     const uint8_t* lab;   // [nk][nj][ni] labels (global material index)
-    const float4* cellc;  // [(nk+1)][(nj+1)][(ni+1)][2] per-cell filter coefficients (ALU sampler)
+    const float4* cellc;  // [(nk+1)][(nj+1)][(ni+1)][2] per-cell filter coefficients (ALU sampler), z-slices interleaved
     const uint2* celll;   // [(nk+1)][(nj+1)][(ni+1)]    per-cell 8 corner labels
     const uint8_t* cellcode;  // same shape: the label if all 8 corners agree and the cell is interior, else 0xFF
     cudaTextureObject_t tex;

@@ -40,8 +40,9 @@ __device__ __forceinline__ void reload_cell(const VolDev& vol, float x, float y,
     size_t cell = ((size_t)ck * (vol.nj + 1) + cj) * (vol.ni + 1) + ci;
     cs.lab8 = __ldg(vol.celll + cell);
     if (!USE_TEX) {
-        cs.c0 = __ldg(vol.cellc + 2 * cell);
-        cs.c1 = __ldg(vol.cellc + 2 * cell + 1);
+        const float4 A = __ldg(vol.cellc + 2 * cell), B = __ldg(vol.cellc + 2 * cell + 1);  // slices stored interleaved
+        cs.c0 = make_float4(A.x, A.z, B.x, B.z);
+        cs.c1 = make_float4(A.y, A.w, B.y, B.w);
     }
     unsigned l0 = cs.lab8.x & 0xFF;
     bool uniform = (cs.lab8.x == cs.lab8.y) && (cs.lab8.x == l0 * 0x01010101u);

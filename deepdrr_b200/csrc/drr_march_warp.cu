@@ -27,13 +27,17 @@
 #ifndef SEG_TEX
 #define SEG_TEX 64                     // steps per segment, TEX sampler (stages label codes only)
 #endif
+#ifndef MAXC
 #define MAXC 256                       // cells staged per warp and segment (ALU sampler: 32 B record + 1 B code each)
+#endif
 #define WARP_SMEM (MAXC * 32 + MAXC)   // coefficient records + codes
 #define MAXC_TEX WARP_SMEM             // the TEX sampler uses the whole buffer for codes
 #ifndef MIN_BLOCKS
 #define MIN_BLOCKS 3
 #endif
+#ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 8
+#endif
 
 // ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
 template <int NM>
@@ -171,20 +175,46 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
         bool same = true;
         {
             const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
-            for (int e = lane; e < ncell; e += 32) {
+            auto cell_of = [&](int e) {
                 int row = (int)(((float)e + 0.5f) * inv_nx);  // e / nx (exact for e < 2^16)
                 int cx = e - row * nx;
                 int cz = (int)(((float)row + 0.5f) * inv_ny);
                 int cy = row - cz * ny;
-                size_t cell = ((size_t)(blz + cz + 2) * (vol.nj + 1) + (bly + cy + 2)) * (vol.ni + 1) + (blx + cx + 2);
-                const int cc = __ldg(vol.cellcode + cell);
-                s_code[e] = (uint8_t)cc;
-                same = same && (first_code < 0 || cc == first_code);
-                first_code = cc;
-                if (STAGE_COEF) {  // slices interleaved for the packed f32x2 form (hw_trilinear_cell2)
-                    const float4 c0 = __ldg(vol.cellc + 2 * cell), c1 = __ldg(vol.cellc + 2 * cell + 1);
-                    s_coef[2 * e] = make_float4(c0.x, c1.x, c0.y, c1.y);
-                    s_coef[2 * e + 1] = make_float4(c0.z, c1.z, c0.w, c1.w);
+                return ((size_t)(blz + cz + 2) * (vol.nj + 1) + (bly + cy + 2)) * (vol.ni + 1) + (blx + cx + 2);
+            };
+            if (STAGE_COEF) {
+                // all loads of the segment are put in flight at once: the 32 B records go global -> shared with
+                // cp.async (no registers, no per-iteration round trip), the label codes through registers
+                int cc[MAXC / 32];
+#pragma unroll
+                for (int k = 0; k < MAXC / 32; k++) {
+                    const int e = lane + 32 * k;
+                    cc[k] = -1;
+                    if (e < ncell) {
+                        const size_t cell = cell_of(e);
+                        cc[k] = __ldg(vol.cellcode + cell);
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_coef + 2 * e);
+                        const float4* src = vol.cellc + 2 * cell;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 1));
+                    }
+                }
+                asm volatile("cp.async.commit_group;");
+#pragma unroll
+                for (int k = 0; k < MAXC / 32; k++) {
+                    if (cc[k] >= 0) {
+                        s_code[lane + 32 * k] = (uint8_t)cc[k];
+                        same = same && (first_code < 0 || cc[k] == first_code);
+                        first_code = cc[k];
+                    }
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else {
+                for (int e = lane; e < ncell; e += 32) {
+                    const int cc = __ldg(vol.cellcode + cell_of(e));
+                    s_code[e] = (uint8_t)cc;
+                    same = same && (first_code < 0 || cc == first_code);
+                    first_code = cc;
                 }
             }
         }
