@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("DRR_B200_LIB") or os.path.join(_HERE, "libdrr_b200.so
 
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1
+MESH_QUERY_HITS, MESH_QUERY_TRAVEL, MESH_QUERY_SEG = 0, 1, 2
 SAMPLER_ALU, SAMPLER_TEX, SAMPLER_HYBRID = 0, 1, 2
 POST_NEGLOG, POST_NOISE, POST_CLIP, POST_COLLECTED = 1, 2, 4, 8
 TUNE_TEX_EIGHTHS, TUNE_KERNEL_VARIANT = 0, 1
@@ -25,7 +26,7 @@ MAX_VOLUMES, MAX_MATERIALS = 8, 16
 # every symbol include/drr_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "drr_create", "drr_destroy", "drr_last_error", "drr_set_stream", "drr_set_spectrum", "drr_add_volume", "drr_add_volume_hu",
-    "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_tuning", "drr_set_mesh_buffers", "drr_set_meshes", "drr_set_mesh_poses", "drr_mesh_clean_hits", "drr_set_scatter_tables", "drr_scatter", "drr_postprocess",
+    "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_tuning", "drr_set_mesh_buffers", "drr_set_meshes", "drr_set_mesh_poses", "drr_mesh_clean_hits", "drr_mesh_query", "drr_set_scatter_tables", "drr_scatter", "drr_postprocess",
     "drr_project", "drr_last_timing", "drr_last_sample_count", "drr_launch_count", "drr_synchronize", "drr_version",
 ]
 
@@ -63,6 +64,7 @@ def load() -> ctypes.CDLL:
     lib.drr_set_meshes.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, ci, ci]
     lib.drr_set_mesh_poses.argtypes = [vp, ci, vp, vp, cf]
     lib.drr_mesh_clean_hits.argtypes = [vp, vp, vp, ci, ci, cf, ci]
+    lib.drr_mesh_query.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci]
     lib.drr_set_scatter_tables.argtypes = [vp, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]
     lib.drr_scatter.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint64, ci, ci, vp, vp, vp, vp, vp, vp, ci]
     lib.drr_postprocess.argtypes = [vp, vp, vp, ci, ci, ci, cu, cf, cf, ctypes.c_uint64, ci]

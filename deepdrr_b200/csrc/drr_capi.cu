@@ -45,6 +45,9 @@ cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_w
                                      cudaStream_t s);
 cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s);
 cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s);
+cudaError_t drr_launch_mesh_cover(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                  int n_prims, int W, int H, uint8_t* out, cudaStream_t s);
+cudaError_t drr_launch_mesh_travel_finish(const float* rg, int npix, float* out, cudaStream_t s);
 
 struct ScatterTables {
     int n_mat, n_e;
@@ -655,6 +658,71 @@ int drr_scatter(drr_ctx* c, unsigned long long n_photons, unsigned long long pho
     CU(c, cudaStreamSynchronize(s));
     CU(c, cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]));
     return DRR_OK;
+}
+
+int drr_mesh_query(drr_ctx* c, int mode, int W, int H, const float* w2i, const uint8_t* select, void* out, int mem_kind) {
+    if (!c) return DRR_E_INVALID;
+    if (c->n_prims == 0) return fail(c, DRR_E_STATE, "drr_mesh_query: call drr_set_meshes first");
+    if (c->pose_views < 1) return fail(c, DRR_E_STATE, "drr_mesh_query: call drr_set_mesh_poses first");
+    if (mode < 0 || mode > 2 || W <= 0 || H <= 0 || !w2i || !select || !out) return fail(c, DRR_E_INVALID, "drr_mesh_query: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t npix = (size_t)W * H;
+    const int MH = c->own_max_hits, np = c->n_prims;
+    // a private copy of the primitive table with the selection folded into the flags the tracing kernels test
+    std::vector<MeshPrimDev> prims(c->h_prims);
+    for (int p = 0; p < np; p++) {
+        MeshPrimDev& d = prims[p];
+        const bool sel = select[p] != 0;
+        if (mode == DRR_MESH_QUERY_TRAVEL) {
+            d.additive = (sel && d.additive && d.layer == 0) ? 1 : 0;  // renderer.py:312-319 with layer_idx=0
+            d.subtractive = 0; d.mat_slot = 0; d.density = 1.0f; d.layer = 0;
+        } else {
+            d.additive = 0; d.subtractive = sel ? 1 : 0; d.layer = 0;
+        }
+    }
+    const size_t out_bytes = mode == DRR_MESH_QUERY_HITS ? npix * MH * 4 : (mode == DRR_MESH_QUERY_TRAVEL ? npix * 4 : npix);
+    const size_t scratch_bytes = mode == DRR_MESH_QUERY_HITS ? npix * MH : (mode == DRR_MESH_QUERY_TRAVEL ? npix * 8 : 0);
+    MeshPrimDev* d_prims = nullptr; ViewDev* d_view = nullptr; float *d_wfm = nullptr, *d_src = nullptr, *d_vw = nullptr;
+    void *d_out = nullptr, *d_scratch = nullptr; int8_t* d_valid = nullptr;
+    int rc = DRR_OK;
+    ViewDev hv; memset(&hv, 0, sizeof hv); memcpy(hv.w2i, w2i, 36);
+#define QCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, DRR_E_CUDA, "drr_mesh_query: %s", cudaGetErrorString(e_)); goto done; } } while (0)
+    QCU(cudaMalloc(&d_prims, sizeof(MeshPrimDev) * np));
+    QCU(cudaMalloc(&d_view, sizeof(ViewDev)));
+    QCU(cudaMalloc(&d_wfm, sizeof(float) * 12 * np));
+    QCU(cudaMalloc(&d_src, 12));
+    QCU(cudaMalloc(&d_vw, sizeof(float) * 9 * (size_t)c->n_tris));
+    QCU(cudaMalloc(&d_valid, 1));
+    if (scratch_bytes) QCU(cudaMalloc(&d_scratch, scratch_bytes));
+    if (mem_kind == DRR_MEM_HOST) QCU(cudaMalloc(&d_out, out_bytes)); else d_out = out;
+    QCU(cudaMemcpyAsync(d_prims, prims.data(), sizeof(MeshPrimDev) * np, cudaMemcpyHostToDevice, s));
+    QCU(cudaMemcpyAsync(d_view, &hv, sizeof hv, cudaMemcpyHostToDevice, s));
+    QCU(cudaMemcpyAsync(d_wfm, c->h_world_from_mesh.data(), sizeof(float) * 12 * np, cudaMemcpyHostToDevice, s));
+    QCU(cudaMemcpyAsync(d_src, c->h_source_world.data(), 12, cudaMemcpyHostToDevice, s));
+    QCU(cudaMemsetAsync(d_valid, 0, 1, s));
+    QCU(drr_launch_mesh_transform(c->d_verts_local, c->d_prim_of_tri, d_wfm, c->n_tris, np, 1, d_vw, s));
+    c->launches += 1;
+    if (mode == DRR_MESH_QUERY_HITS) {
+        QCU(drr_launch_mesh_subtractive(d_view, d_src, d_vw, d_prims, np, c->n_tris, 0, 1, W, H, 1, MH, c->far_limit, (float*)d_out,
+                                        (int8_t*)d_scratch, s));
+        c->launches += 1;
+    } else if (mode == DRR_MESH_QUERY_TRAVEL) {
+        QCU(cudaMemsetAsync(d_scratch, 0, scratch_bytes, s));
+        QCU(drr_launch_mesh_additive(d_view, d_src, d_vw, d_prims, np, c->n_tris, 1, 1, W, H, 1, MH, d_valid, nullptr, nullptr, (float*)d_scratch, s));
+        QCU(drr_launch_mesh_travel_finish((const float*)d_scratch, (int)npix, (float*)d_out, s));
+        c->launches += 2;
+    } else {
+        QCU(drr_launch_mesh_cover(d_view, d_src, d_vw, d_prims, np, W, H, (uint8_t*)d_out, s));
+        c->launches += 1;
+    }
+    if (mem_kind == DRR_MEM_HOST) QCU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    QCU(cudaStreamSynchronize(s));
+#undef QCU
+done:
+    cudaFree(d_prims); cudaFree(d_view); cudaFree(d_wfm); cudaFree(d_src); cudaFree(d_vw); cudaFree(d_valid); cudaFree(d_scratch);
+    if (mem_kind == DRR_MEM_HOST) cudaFree(d_out);
+    return rc;
 }
 
 int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n, float far_limit, int mem_kind) {

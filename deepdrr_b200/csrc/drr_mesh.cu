@@ -227,6 +227,47 @@ __global__ void __launch_bounds__(128) mesh_additive_kernel(const ViewDev* __res
     }
 }
 
+// Coverage mask (project_seg): 255 where any triangle of a selected primitive is hit, front or back face.
+__global__ void __launch_bounds__(128) mesh_cover_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
+                                                         const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
+                                                         int n_prims, int W, int H, uint8_t* __restrict__ out) {
+    __shared__ float s_v[MESH_CHUNK * 9];
+    const int tiles_x = (W + 15) / 16;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
+    const bool ok = udx < W && vdx < H;
+    Ray r = make_ray(views[0].w2i, min(udx, W - 1), min(vdx, H - 1));
+    const float3 d = make_float3(r.rx, r.ry, r.rz);
+    const float3 o = make_float3(source_world[0], source_world[1], source_world[2]);
+    bool hit = false;
+    for (int p = 0; p < n_prims; p++) {
+        const MeshPrimDev pr = prims[p];
+        if (!pr.subtractive) continue;  // the query marks the selected primitives this way
+        for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
+            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = verts_world[(size_t)base * 9 + i];
+            __syncthreads();
+            if (!ok || hit) continue;
+            for (int k = 0; k < cnt && !hit; k++) {
+                float t; bool entering;
+                hit = ray_tri(o, d, s_v + 9 * k, t, entering);
+            }
+        }
+    }
+    if (ok) out[(size_t)vdx * W + udx] = hit ? 255 : 0;
+}
+
+// project_travel epilogue (projector.py:1048-1051): drop unbalanced and negative pixels.
+__global__ void mesh_travel_finish_kernel(const float* __restrict__ rg, int npix, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float v = rg[2 * i];
+    if (fabsf(rg[2 * i + 1]) > 0.01f) v = 0.0f;
+    if (v < 0.0f) v = 0.0f;
+    out[i] = v;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 cudaError_t drr_launch_mesh_transform(const float* verts_local, const int* prim_of_tri, const float* world_from_mesh, int n_tris, int n_prims,
                                       int n_views, float* verts_world, cudaStream_t s) {
@@ -256,5 +297,16 @@ cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_w
 
 cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s) {
     tide_clean_kernel<<<(n_rays + 63) / 64, 64, 0, s>>>(ts, facing, n_rays, n, far_limit);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_mesh_cover(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
+                                  int n_prims, int W, int H, uint8_t* out, cudaStream_t s) {
+    mesh_cover_kernel<<<((W + 15) / 16) * ((H + 7) / 8), 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, W, H, out);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_mesh_travel_finish(const float* rg, int npix, float* out, cudaStream_t s) {
+    mesh_travel_finish_kernel<<<(npix + 255) / 256, 256, 0, s>>>(rg, npix, out);
     return cudaGetLastError();
 }

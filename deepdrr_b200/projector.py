@@ -465,6 +465,98 @@ class Projector(object):
                                    0, None, None, _lib.ptr(area), mem), h)
         return area
 
+    # ------------------------------------------------------------------ mesh queries (reference :882-1053)
+    def _mesh_query(self, proj, mode: int, select: np.ndarray):
+        """One drr_mesh_query call for the primitives flagged in ``select`` (same pose path as ``_run``)."""
+        lib, h = _lib.load(), self._h
+        W, H = (int(x) for x in proj.intrinsic.sensor_size)
+        if self._sensor_fixed not in (None, (W, H)):
+            raise RuntimeError("Changing sensor size while using meshes is not yet supported.")  # reference :1359-1363
+        self._upload_meshes()
+        wfm = np.ascontiguousarray(np.stack([np.asarray(m.world_from_ijk.toarray(), dtype=np.float32).reshape(12) for m in self.meshes])[None])
+        sw = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32).reshape(1, 3)
+        _lib.check(lib.drr_set_mesh_poses(h, 1, _lib.ptr(wfm), _lib.ptr(sw), float(self.source_to_detector_distance * 2)), h)
+        w2i = np.ascontiguousarray(np.asarray(proj.world_from_index, dtype=np.float64)[:3, :3], dtype=np.float32).reshape(9)
+        sel = np.ascontiguousarray(select, dtype=np.uint8)
+        if mode == _lib.MESH_QUERY_HITS:
+            out = np.empty((H, W, int(self.max_mesh_hits)), dtype=np.float32)
+        elif mode == _lib.MESH_QUERY_TRAVEL:
+            out = np.empty((H, W), dtype=np.float32)
+        else:
+            out = np.empty((H, W), dtype=np.uint8)
+        _lib.check(lib.drr_mesh_query(h, mode, W, H, _lib.ptr(w2i), _lib.ptr(sel), _lib.ptr(out), _lib.MEM_HOST), h)
+        return out
+
+    def _select(self, tag) -> np.ndarray:
+        """Primitives a pass with ``tags=tag`` draws: ``None`` keeps all, otherwise equality with the primitive's tag
+        (reference renderer.py:318-324).  Disabled meshes are never drawn (renderer.py:289-290)."""
+        return np.array([bool(getattr(m, "enabled", True)) and (tag is None or m.tag == tag) for m in self.meshes], dtype=np.uint8)
+
+    def _one_view(self, camera_projections):
+        if len(camera_projections) > 1:
+            raise NotImplementedError("multiple projections")
+        if not self.meshes:
+            raise RuntimeError("this projector has no meshes")
+        return self._prepare_project(camera_projections)[0]
+
+    def project_seg(self, *camera_projections, tags=None):
+        """Coverage mask per tag: list of ``[H, W]`` uint8 images, 255 where a primitive carrying ``tags[c]`` is hit.
+
+        Reference: :945-971, :1090-1122 (SEG passes, four tags per RGBA render) -- here one ray-triangle pass per tag.
+        """
+        proj = self._one_view(camera_projections)
+        if tags is None:
+            raise TypeError("project_seg needs a list of tags")  # the reference fails on len(None), :1108
+        return [self._mesh_query(proj, _lib.MESH_QUERY_SEG, self._select(t) if t is not None else np.zeros(len(self.meshes), np.uint8))
+                for t in tags]
+
+    def project_hits(self, *camera_projections, tags=None):
+        """Per tag, the ``[H, W, max_mesh_hits]`` float32 list of (entry, exit, ...) distances along each pixel's ray
+        (mm from the source, nearest first, ``inf`` padded); every primitive with the tag counts, whatever its flags.
+
+        Reference: :973-1015 (dual depth peeling with force_all_subtract + kernelReorder / kernelTide).
+        """
+        proj = self._one_view(camera_projections)
+        return [] if tags is None else [self._mesh_query(proj, _lib.MESH_QUERY_HITS, self._select(t)) for t in tags]
+
+    def project_travel(self, *camera_projections, tags=None):
+        """Per tag, the ``[H, W]`` float32 path length (mm) inside the additive layer-0 primitives with the tag.
+
+        Reference: :1017-1053 (density pass with ``density_override=1``; unbalanced or negative pixels zeroed).
+        """
+        proj = self._one_view(camera_projections)
+        return [] if tags is None else [self._mesh_query(proj, _lib.MESH_QUERY_TRAVEL, self._select(t)) for t in tags]
+
+    def meshes_bounding_sphere_in_frustum(self, meshes, index_from_world=None):
+        """Per mesh: does its loose bounding sphere touch the view frustum (four side planes through the source)?
+
+        Reference: :882-943.  The planes there come from un-projecting the mid-edge NDC points of the GL camera whose
+        principal point is ``(cx, H - cy)`` (:859-862); in camera coordinates that is the pixel ray ``((u - cx) / fx,
+        (v - cy) / fy, 1)`` for the mid points of the four detector edges, which is what is evaluated here.
+        """
+        if index_from_world is None:
+            proj = self._prepare_project(())[0]
+        else:
+            self._prepare_project((index_from_world,))
+            proj = index_from_world
+        k = proj.intrinsic
+        W, H = (float(x) for x in k.sensor_size)
+        top, bottom = (H - k.cy) / k.fy, (0.0 - k.cy) / k.fy
+        left, right = (0.0 - k.cx) / k.fx, (W - k.cx) / k.fx
+        planes = []  # (normal, ) in camera coordinates with z pointing away from the detector (GL convention)
+        for n in ((0.0, 1.0, top), (0.0, -1.0, -bottom), (-1.0, 0.0, -left), (1.0, 0.0, right)):
+            n = np.asarray(n, dtype=np.float64)
+            planes.append(n / np.linalg.norm(n))
+        E = np.asarray(proj.extrinsic.toarray() if hasattr(proj.extrinsic, "toarray") else proj.extrinsic, dtype=np.float64)
+        res = []
+        for mesh in meshes:
+            center, radius = mesh.get_loose_bounding_sphere
+            c_world = np.asarray(mesh.world_from_ijk.toarray(), dtype=np.float64) @ np.array([center[0], center[1], center[2], 1.0])
+            c_cam = E[:3, :3] @ c_world[:3] + E[:3, 3]
+            c_cam[2] = -c_cam[2]
+            res.append(bool(all(float(np.dot(c_cam, n)) < radius for n in planes)))
+        return res
+
     # ------------------------------------------------------------------ introspection used by bench / tests
     def last_timing_ms(self):
         t = (ctypes.c_float * 3)()

@@ -233,6 +233,18 @@ class Mesh(Renderable):
     def get_center(self) -> np.ndarray:
         return self.anatomical_from_IJK @ self.vertices.mean(axis=0).astype(np.float64)
 
+    @property
+    def get_bounding_AABB(self):
+        """(min corner, max corner) of the vertices, mesh-local (reference vol/mesh.py:142-147)."""
+        return self.vertices.min(axis=0).astype(np.float64), self.vertices.max(axis=0).astype(np.float64)
+
+    @property
+    def get_loose_bounding_sphere(self):
+        """(centre of the AABB, distance to the farthest vertex), mesh-local (reference vol/mesh.py:149-162)."""
+        lo, hi = self.get_bounding_AABB
+        center = (lo + hi) / 2
+        return center, float(np.max(np.linalg.norm(self.vertices.astype(np.float64) - center, axis=1)))
+
     @classmethod
     def from_stl(cls, path, **kwargs) -> "Mesh":
         """Binary or ASCII STL reader (the reference loads STLs through trimesh / pyvista, vol/mesh.py:91-140)."""

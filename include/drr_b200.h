@@ -124,6 +124,23 @@ int drr_set_mesh_poses(drr_ctx* ctx, int n_views, const float* world_from_mesh, 
 /* Replaces: kernelTide (peel_postprocess_kernel.cu:15-177) from its cut-off step on: cleans n_rays hit
  * lists of n (<= 128) slots (distance, facing: +1 entry / -1 exit / 0 empty) in place. */
 int drr_mesh_clean_hits(drr_ctx* ctx, float* ts, int8_t* facing, int n_rays, int n, float far_limit, int mem_kind);
+/* Replaces: Projector.project_seg / project_hits / project_travel (projector.py:945-1053) for one view of the
+ * primitives selected by `select` [n_prims] (u8, non-zero = the primitive carries the requested tag):
+ *   DRR_MESH_QUERY_HITS   -> out f32 [H*W][max_mesh_hits]: cleaned (entry, exit, ...) distances, +inf padded; every
+ *                            selected primitive counts as subtractive, whatever its layer (renderer.py:312-324,
+ *                            force_all_subtract), then kernelReorder/kernelTide (projector.py:1144-1250);
+ *   DRR_MESH_QUERY_TRAVEL -> out f32 [H*W]: path length (mm) inside the selected additive layer-0 primitives
+ *                            (density pass with density_override=1, projector.py:1027-1053), 0 where the
+ *                            entry/exit count does not balance (|G| > 0.01) or the sum is negative;
+ *   DRR_MESH_QUERY_SEG    -> out u8 [H*W]: 255 where any triangle of a selected primitive covers the pixel
+ *                            (segmentation.frag with GL_MAX blending, renderer.py:326-333, 437-446).
+ * Poses come from the last drr_set_mesh_poses (its first view); world_from_index is that view's 3x3.
+ * `out` is host or device memory (mem_kind). */
+#define DRR_MESH_QUERY_HITS 0
+#define DRR_MESH_QUERY_TRAVEL 1
+#define DRR_MESH_QUERY_SEG 2
+int drr_mesh_query(drr_ctx* ctx, int mode, int width, int height, const float* world_from_index, const uint8_t* select,
+                   void* out, int mem_kind);
 
 /* Monte Carlo scatter (north_star kernel 3).  The reference has no scatter kernel any more (projector.py:530-531
  * raises); these entry points take its MC-GPU data tables (mcgpu_mfp_data.py, mcgpu_rita_samplers.py,

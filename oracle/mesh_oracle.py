@@ -138,3 +138,44 @@ def mesh_buffers(prims, w2i, source_world, W, H, n_layers, max_hits, far_limit, 
                 additive[p["layer"], slot, :, 0] += np.where(valid, res, 0.0).sum(axis=1)
     return {"hit_alphas": hit_alphas, "hit_facing": hit_facing, "layer_valid": layer_valid, "additive": additive.astype(np.float32),
             "mesh_mats": np.array(mesh_mats, dtype=np.int32)}
+
+
+def query(prims, select, mode, w2i, source_world, W, H, max_hits, far_limit):
+    """Restatement of Projector.project_hits / project_travel / project_seg for one tag (reference
+    projector.py:945-1053; renderer.py:312-333 for which primitives a pass draws).
+    prims as in mesh_buffers; select [n_prims] bool.  mode "hits" -> [H, W, max_hits] f32, "travel" -> [H, W] f32,
+    "seg" -> [H, W] u8.  Also returns the per-pixel hit count of the drawn primitives (silhouette detection)."""
+    dirs = pixel_dirs(w2i, W, H)
+    npix = W * H
+    if mode == "travel":
+        drawn = [p for p, s in zip(prims, select) if s and p["additive"] and p["layer"] == 0]
+    else:
+        drawn = [p for p, s in zip(prims, select) if s]
+    traced = [trace(p["tris_world"], source_world, dirs) for p in drawn]
+    count = np.zeros(npix, dtype=np.int64)
+    for t, _ in traced:
+        count += np.isfinite(t).sum(axis=1)
+    if mode == "seg":
+        return np.where(count > 0, 255, 0).astype(np.uint8).reshape(H, W), count.reshape(H, W)
+    if mode == "travel":
+        R, G = np.zeros(npix), np.zeros(npix)
+        for t, ent in traced:
+            s = np.where(ent, -1.0, 1.0)
+            fin = np.isfinite(t)
+            R += np.where(fin, np.where(fin, t, 0.0) * s, 0.0).sum(axis=1)
+            G += np.where(fin, s, 0.0).sum(axis=1)
+        out = np.where(np.abs(G) > 0.01, 0.0, R)
+        return np.maximum(out, 0.0).astype(np.float32).reshape(H, W), count.reshape(H, W)
+    out = np.full((npix, max_hits), np.inf, dtype=np.float32)
+    for px in range(npix):
+        ts, fs = [], []
+        for t, ent in traced:
+            k = np.nonzero(np.isfinite(t[px]))[0]
+            ts += list(t[px, k]); fs += [1 if e else -1 for e in ent[px, k]]
+        if not ts:
+            continue
+        order = np.argsort(ts, kind="stable")[:max_hits]
+        lt = np.full(max_hits, np.inf, dtype=np.float32); lf = np.zeros(max_hits, dtype=np.int8)
+        lt[:len(order)] = np.array(ts, dtype=np.float32)[order]; lf[:len(order)] = np.array(fs, dtype=np.int8)[order]
+        out[px], _ = tide_clean(lt, lf, far_limit)
+    return out.reshape(H, W, max_hits), count.reshape(H, W)

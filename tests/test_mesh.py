@@ -233,3 +233,95 @@ def test_mesh_only_sphere_chord_and_enable_toggle():
     ok = (hits == 2) & (np.abs(a - path) < 1e-3)
     assert ok.sum() > 0.95 * (hits == 2).sum()
     assert np.abs(a - path)[ok].max() <= 1e-5 * 12.0
+
+
+def _query_scene():
+    sv, sf = phantoms.screw_mesh(rings_per_mm=0.5, segments=16)
+    screw = Mesh(sv, sf, material="titanium", tag="implant")
+    phantoms.place_kwire(screw, (-20.0, -30.0, 10.0), (0.2, 1.0, 0.1))
+    bv, bf = phantoms.icosphere(35.0, 2)
+    ball = Mesh(bv, bf, material="lung", density=0.3, subtractive=True, additive=False, layer=1, tag="cavity")
+    ball.translate((40.0, 10.0, -5.0))
+    iv, if_ = phantoms.icosphere(20.0, 2)
+    inner = Mesh(iv, if_, material="bone", layer=0, tag="implant")           # overlaps nothing of the screw
+    inner.translate((25.0, 10.0, -5.0))
+    ov, of = phantoms.box_mesh((10.0, 10.0, 10.0))
+    other = Mesh(ov, of, material="iron", layer=0)                           # untagged
+    other.translate((-40.0, 0.0, 30.0))
+    return [screw, ball, inner, other]
+
+
+@pytest.mark.gpu
+def test_project_hits_travel_seg_match_restatement():
+    """project_hits / project_travel / project_seg (reference projector.py:945-1053) per tag vs oracle.mesh_oracle.query."""
+    meshes = _query_scene()
+    W = H = 48
+    k = geo.CameraIntrinsicTransform.from_sizes((W, H), 4.0, 1000.0)
+    pose = phantoms.look_at_projection((30.0, -520.0, 10.0), (-0.03, 1.0, 0.0), (0, 0, 1), k)
+    with Projector(meshes, camera_intrinsics=k, source_to_detector_distance=1000.0, neglog=False, max_mesh_hits=16) as p:
+        tags = ["implant", "cavity", None, "nothing"]
+        hits = p.project_hits(pose, tags=tags)
+        travel = p.project_travel(pose, tags=tags)
+        seg = p.project_seg(pose, tags=["implant", "cavity", "nothing"])
+        assert p.project_hits(pose) == [] and p.project_travel(pose) == []
+        with pytest.raises(NotImplementedError):
+            p.project_hits(pose, pose, tags=tags)
+        all_mats = p.all_materials
+    prims = _prims_for_oracle(meshes, all_mats)
+    w2i, _, _ = geo.pose_arrays(pose, [])
+    src = pose.center_in_world
+    for i, tag in enumerate(tags):
+        sel = [tag is None or m.tag == tag for m in meshes]
+        eh, cnt = mesh_oracle.query(prims, sel, "hits", w2i, src, W, H, 16, 2000.0)
+        # silhouettes (fp32 vs fp64 edge tests disagree on the hit count) show up as a different number of finite slots
+        same = np.isfinite(hits[i]).sum(axis=2) == np.isfinite(eh).sum(axis=2)
+        assert same.mean() > 0.97
+        a, b = hits[i][same], eh[same]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        assert np.all(np.abs(a[fin] - b[fin]) <= 8 * 6.1e-5)
+        assert hits[i].dtype == np.float32 and hits[i].shape == (H, W, 16)
+        et, cnt_t = mesh_oracle.query(prims, sel, "travel", w2i, src, W, H, 16, 2000.0)
+        good = np.abs(travel[i] - et) <= 16 * 6.1e-5 + 1e-5 * et
+        assert good.mean() > 0.97 and travel[i].min() >= 0
+        if tag == "nothing":
+            assert np.all(np.isinf(hits[i])) and np.all(travel[i] == 0)
+        if tag == "cavity":                     # subtractive-only primitive: counted by hits, not drawn by the density pass
+            assert np.all(travel[i] == 0) and np.isfinite(hits[i]).any()
+    for i, tag in enumerate(["implant", "cavity", "nothing"]):
+        sel = [m.tag == tag for m in meshes]
+        es, cnt = mesh_oracle.query(prims, sel, "seg", w2i, src, W, H, 16, 2000.0)
+        assert seg[i].dtype == np.uint8 and set(np.unique(seg[i])) <= {0, 255}
+        assert (seg[i] == es).mean() > 0.985
+        interior = cnt >= 2
+        assert np.all(seg[i][interior & (es == 255)] == 255) or (seg[i] == es)[interior].mean() > 0.995
+    assert seg[2].max() == 0 and seg[0].max() == 255
+    # implant travel: closed additive meshes -> hits interval lengths add up to the travel length
+    ih = hits[0]
+    with np.errstate(invalid="ignore"):
+        length = np.where(np.isfinite(ih[..., 1::2]), ih[..., 1::2] - ih[..., 0::2], 0.0).sum(axis=2)
+    both = (np.isfinite(ih).sum(axis=2) % 2 == 0) & (travel[0] > 0)
+    assert np.abs(length - travel[0])[both].max() < 1e-2
+
+
+def test_bounding_sphere_in_frustum():
+    """meshes_bounding_sphere_in_frustum (reference projector.py:882-943): sphere vs the four side planes."""
+    from deepdrr_b200 import _lib
+    v, f = phantoms.icosphere(10.0, 1)
+    k = geo.CameraIntrinsicTransform.from_sizes((64, 48), 2.0, 1000.0)   # detector 128 x 96 mm at 1000 mm
+    pose = phantoms.look_at_projection((0, -500.0, 0), (0, 1.0, 0), (0, 0, 1), k)
+    p = Projector.__new__(Projector)
+    p.initialized, p.device = True, None
+    p._source_to_detector_distance = 1000.0
+    def at(x, y, z):
+        m = Mesh(v, f, material="iron")
+        m.translate((x, y, z))
+        return m
+    # at y = 0 the frustum half-widths are 500 * 64/1000 = 32 mm (u) and 24 mm (v)
+    axes = np.linalg.inv(pose.extrinsic.data)[:3, :3]       # camera x, y, z axes in world
+    cx, cy = axes[:, 0], axes[:, 1]
+    inside, touching, outside_u, outside_v, behind_edge = at(0, 0, 0), at(*(cx * 41.0)), at(*(cx * 43.0)), at(*(cy * 35.0)), at(*(cy * 33.0))
+    res = p.meshes_bounding_sphere_in_frustum([inside, touching, outside_u, outside_v, behind_edge], pose)
+    assert res == [True, True, False, False, True]
+    r = inside.get_loose_bounding_sphere[1]
+    assert abs(r - 10.0) < 1e-4
