@@ -8,11 +8,13 @@ Only what the projection path consumes from the reference's ``deepdrr.vol`` pack
 * ``enabled`` flag                                                           (vol/volume.py:190-192)
 
 plus the two conversions the synthetic configs need: HU -> density (vol/volume.py:338-351) and
-threshold segmentation (load_dicom.py:132-143).  Loaders (NIfTI/NRRD/DICOM), mesh tooling and the
+threshold segmentation (load_dicom.py:132-143), and the NIfTI / NRRD loaders (``Volume.from_nifti`` /
+``from_nrrd``, vol/volume.py:581-696, 848-895; file parsing in ``formats.py``).  DICOM, mesh tooling and the
 V-Net segmentation are out of scope.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple, Union
 
 import numpy as np
@@ -125,6 +127,68 @@ class Volume(Renderable):
         data = convert_hounsfield_to_density(hu_values)
         materials = segment_materials_thresholding(hu_values)
         return cls(data, materials, anatomical_from_IJK, world_from_anatomical, **kwargs)
+
+    @classmethod
+    def from_nifti(cls, path, world_from_anatomical=None, use_thresholding: bool = True, use_cached: bool = True,
+                   save_cache: bool = False, cache_dir=None, materials=None, segmentation: bool = False, label=None,
+                   binarize: bool = False, density_kwargs: Optional[dict] = None, **kwargs):
+        """Load a CT (HU) or a segmentation from a NIfTI-1 file (reference: vol/volume.py:581-696).
+
+        ``anatomical_from_IJK`` is the file's affine (RAS).  Only threshold segmentation exists here
+        (``use_thresholding=False`` is the reference's V-Net, out of scope); the cache arguments are accepted and unused.
+        ``materials`` may map names to boolean arrays or to NIfTI paths of masks (> 0).
+        """
+        from . import formats
+        values, affine, _ = formats.read_nifti(path)
+        anatomical_from_IJK = geo.FrameTransform(affine)
+        if segmentation:
+            if label is None:
+                seg = values > 0
+            elif isinstance(label, (int, np.integer, float)):
+                seg = values == label
+            elif isinstance(label, list):
+                seg = np.isin(values, label)
+            else:
+                raise ValueError(f"Invalid label: {label}")
+            materials = dict(bone=seg)
+            data = seg.astype(np.float32) if binarize else values.astype(np.float32)
+        else:
+            data = convert_hounsfield_to_density(values, **(density_kwargs or {}))
+            if materials is None:
+                if not use_thresholding:
+                    raise NotImplementedError("only threshold segmentation is available (the V-Net segmenter is out of scope)")
+                materials = segment_materials_thresholding(values)
+            else:
+                materials = dict(materials)
+                for m in materials:
+                    if isinstance(materials[m], (str, os.PathLike)):
+                        if not os.path.exists(materials[m]):
+                            raise ValueError(f"Could not find material {m} at {materials[m]}")
+                        materials[m] = formats.read_nifti(materials[m])[0] > 0
+                    else:
+                        materials[m] = np.asarray(materials[m]).astype(bool)
+        return cls(data, materials, anatomical_from_IJK=anatomical_from_IJK, world_from_anatomical=world_from_anatomical,
+                   anatomical_coordinate_system="RAS", **kwargs)
+
+    @classmethod
+    def from_nrrd(cls, path, world_from_anatomical=None, use_thresholding: bool = True, use_cached: bool = True, cache_dir=None, **kwargs):
+        """Load a CT (HU) from an NRRD file (reference: vol/volume.py:848-895).
+
+        As in the reference, the 3x4 ``[space directions | space origin]`` is used as it stands -- axis i's direction
+        ends up in ROW i -- which equals the usual column convention only for axis-aligned (or symmetric) directions.
+        """
+        from . import formats
+        values, header = formats.read_nrrd(path)
+        if values.ndim != 3:
+            raise ValueError(f"{path}: expected a 3-D volume, got shape {values.shape}")
+        m = np.concatenate([np.asarray(header["space directions"], dtype=np.float64), np.asarray(header["space origin"], dtype=np.float64).reshape(-1, 1)], axis=1)
+        anatomical_from_ijk = geo.FrameTransform(np.concatenate([m, [[0, 0, 0, 1]]], axis=0))
+        if not use_thresholding:
+            raise NotImplementedError("only threshold segmentation is available (the V-Net segmenter is out of scope)")
+        data = convert_hounsfield_to_density(values)
+        materials = segment_materials_thresholding(values)
+        system = {"right-anterior-superior": "RAS", "left-posterior-superior": "LPS"}.get(header.get("space", "right-anterior-superior"))
+        return cls(data, materials, anatomical_from_ijk, world_from_anatomical, anatomical_coordinate_system=system, **kwargs)
 
     @property
     def shape(self) -> Tuple[int, int, int]:
