@@ -45,6 +45,8 @@ cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_w
                                      cudaStream_t s);
 cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s);
 cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s);
+cudaError_t drr_launch_march_multi(const MarchParams& P, int n_sm, cudaStream_t s);
+cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaStream_t s);
 cudaError_t drr_launch_mesh_cover(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
                                   int n_prims, int W, int H, uint8_t* out, cudaStream_t s);
 cudaError_t drr_launch_mesh_travel_finish(const float* rg, int npix, float* out, cudaStream_t s);
@@ -213,6 +215,7 @@ struct drr_ctx {
     float *d_world_from_mesh = nullptr, *d_source_world = nullptr, *d_verts_world = nullptr, *d_own_hit_alphas = nullptr, *d_own_additive = nullptr;
     int8_t* d_own_hit_facing = nullptr;
     size_t wfm_cap = 0, srcw_cap = 0, vw_cap = 0, oha_cap = 0, ohf_cap = 0, oadd_cap = 0;
+    unsigned int* d_worklist = nullptr; size_t worklist_cap = 0;
     // per-batch scratch (grown on demand)
     ViewDev* d_views = nullptr; ViewDev* h_views = nullptr; int views_cap = 0;
     float *d_area = nullptr, *d_intensity = nullptr, *d_pprob = nullptr, *d_scratch = nullptr;
@@ -306,6 +309,7 @@ int drr_destroy(drr_ctx* c) {
     for (void* p : c->sc_owned) cudaFree(p);
     cudaFree(c->d_sc_cdf); cudaFree(c->d_sc_tally); cudaFree(c->d_sc_counters);
     cudaFree(c->d_verts_local); cudaFree(c->d_prim_of_tri); cudaFree(c->d_prims); cudaFree(c->d_own_mesh_mats); cudaFree(c->d_own_layer_valid);
+    cudaFree(c->d_worklist);
     cudaFree(c->d_world_from_mesh); cudaFree(c->d_source_world); cudaFree(c->d_verts_world); cudaFree(c->d_own_hit_alphas);
     cudaFree(c->d_own_additive); cudaFree(c->d_own_hit_facing);
     cudaFree(c->d_energies); cudaFree(c->d_pdf); cudaFree(c->d_mu);
@@ -893,8 +897,30 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         if (V > 4 || M > 8) return fail(c, DRR_E_INVALID, "drr_project: the general kernel supports up to 4 volumes / 8 materials");
         for (int v = 0; v < V; v++)
             if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_project: volume %d has no raw arrays", v);
-        CU(c, drr_launch_march_general(P, s));
-        c->launches += 1;
+        // Tiles whose rays see a single volume take the lock-step kernel; the others are listed for the general one.
+        bool split = V > 1 && !meshes && !c->attenuate_outside && c->variant == 0;
+        int sampler = c->sampler;
+        for (int v = 0; v < V && split; v++) {
+            const VolHost& h = c->vols[v];
+            if (!h.cellcode || (sampler != DRR_SAMPLER_TEX && !h.cellc) || (sampler != DRR_SAMPLER_ALU && !h.tex)) split = false;
+            // Volumes that share a priority all contribute whenever one of them is picked, even outside their own
+            // box (K.cu:540-547 tests the priority only): such scenes are replayed step by step.
+            for (int u = 0; u < v; u++)
+                if (P.enabled[u] && P.enabled[v] && P.priority[u] == P.priority[v]) split = false;
+        }
+        if (split) {
+            const size_t n_tiles = (size_t)((W + 7) / 8) * ((H + 3) / 4) * n_views;
+            if ((rc = ensure(c, (void**)&c->d_worklist, &c->worklist_cap, sizeof(unsigned) * (n_tiles + 2)))) return rc;
+            CU(c, cudaMemsetAsync(c->d_worklist, 0, sizeof(unsigned) * 2, s));
+            P.work_count = c->d_worklist; P.worklist = c->d_worklist + 2;
+            P.tex_eighths = sampler == DRR_SAMPLER_ALU ? 0 : (sampler == DRR_SAMPLER_TEX ? 8 : c->tex_eighths);
+            CU(c, drr_launch_march_multi(P, c->n_sm, s));
+            CU(c, drr_launch_march_general_list(P, c->n_sm * 8, s));
+            c->launches += 2;
+        } else {
+            CU(c, drr_launch_march_general(P, s));
+            c->launches += 1;
+        }
     }
     CU(c, cudaEventRecord(c->ev[2], s));
 

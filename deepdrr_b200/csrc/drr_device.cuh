@@ -51,6 +51,9 @@ struct MarchParams {
     float* area;  // [view][M][H*W]
     unsigned long long* sample_count;
     unsigned int* tile_counter;
+    // multi-volume scenes: 8x4-pixel tiles the lock-step kernel hands over to the general kernel
+    unsigned int* worklist;    // [n_tiles] tile ids
+    unsigned int* work_count;  // [0] entries in the list, [1] consumer cursor
 };
 
 // ---------------------------------------------------------------------------------------------

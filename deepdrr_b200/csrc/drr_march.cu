@@ -214,12 +214,7 @@ __global__ void __launch_bounds__(256) march_single_kernel(const __grid_constant
 // general path: NV volumes, priorities, meshes, outside air
 // ---------------------------------------------------------------------------------------------
 template <int NV, int NM>
-__global__ void __launch_bounds__(128) march_general_kernel(const __grid_constant__ MarchParams P) {
-    const int tiles_x = (P.W + 15) / 16;
-    const int tile = blockIdx.x, view = blockIdx.y;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
-    if (udx >= P.W || vdx >= P.H) return;
+__device__ __forceinline__ void general_ray(const MarchParams& P, const int view, const int udx, const int vdx) {
     const ViewDev& vw = P.views[view];
     const size_t npix = (size_t)P.W * P.H;
     const size_t pix = (size_t)vdx * P.W + udx;
@@ -368,6 +363,38 @@ __global__ void __launch_bounds__(128) march_general_kernel(const __grid_constan
     if ((threadIdx.x & 31) == (__ffs(mask) - 1) && ns) atomicAdd(P.sample_count, ns);
 }
 
+template <int NV, int NM>
+__global__ void __launch_bounds__(128) march_general_kernel(const __grid_constant__ MarchParams P) {
+    const int tiles_x = (P.W + 15) / 16;
+    const int tile = blockIdx.x, view = blockIdx.y;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
+    if (udx >= P.W || vdx >= P.H) return;
+    general_ray<NV, NM>(P, view, udx, vdx);
+}
+
+// The tiles march_multi_kernel (drr_march_warp.cu) could not take: one warp per 8x4 tile, pulled from the work list.
+template <int NV, int NM>
+__global__ void __launch_bounds__(128) march_general_list_kernel(const __grid_constant__ MarchParams P) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n = P.work_count[0];
+    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+    const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(P.work_count + 1, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n) break;
+        const unsigned tile = P.worklist[w];
+        const unsigned view = tile / tiles_per_view;
+        const unsigned tv = tile - view * tiles_per_view;
+        const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
+        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
+        if (udx < P.W && vdx < P.H) general_ray<NV, NM>(P, (int)view, udx, vdx);
+        __syncwarp();
+    }
+}
+
 // NUM_VOLUMES == 0 (mesh-only scenes): the trace block of projectKernel is compiled out (K.cu:252-555) and
 // only the additive mesh densities reach the area densities (K.cu:565-584).
 __global__ void march_meshonly_kernel(const __grid_constant__ MarchParams P) {
@@ -435,6 +462,36 @@ static cudaError_t launch_general_nv(const MarchParams& P, cudaStream_t s) {
         case 6: return launch_general_nvnm<NV, 6>(P, s);
         case 7: return launch_general_nvnm<NV, 7>(P, s);
         case 8: return launch_general_nvnm<NV, 8>(P, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int NV, int NM>
+static cudaError_t launch_general_list_nvnm(const MarchParams& P, int grid, cudaStream_t s) {
+    march_general_list_kernel<NV, NM><<<grid, 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <int NV>
+static cudaError_t launch_general_list_nv(const MarchParams& P, int grid, cudaStream_t s) {
+    switch (P.M) {
+        case 1: return launch_general_list_nvnm<NV, 1>(P, grid, s);
+        case 2: return launch_general_list_nvnm<NV, 2>(P, grid, s);
+        case 3: return launch_general_list_nvnm<NV, 3>(P, grid, s);
+        case 4: return launch_general_list_nvnm<NV, 4>(P, grid, s);
+        case 5: return launch_general_list_nvnm<NV, 5>(P, grid, s);
+        case 6: return launch_general_list_nvnm<NV, 6>(P, grid, s);
+        case 7: return launch_general_list_nvnm<NV, 7>(P, grid, s);
+        case 8: return launch_general_list_nvnm<NV, 8>(P, grid, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaStream_t s) {
+    switch (P.V) {
+        case 2: return launch_general_list_nv<2>(P, grid, s);
+        case 3: return launch_general_list_nv<3>(P, grid, s);
+        case 4: return launch_general_list_nv<4>(P, grid, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -38,6 +38,7 @@
 #ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 8
 #endif
+#define MULTI_MAXV 4                   // volumes the multi-volume variant handles
 
 // ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
 template <int NM>
@@ -75,31 +76,18 @@ __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float 
 
 // KTEX = how many samples of every group of 8 consecutive steps are fetched by the texture unit; the others are
 // interpolated on the FMA pipes from the staged cell records.  8 = TEX only (no records staged), 0 = ALU only.
-template <int NM, int KTEX>
-__device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
-                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps) {
+// MULTI: the scene has more volumes; [olo, ohi] is the hull of this ray's windows in the OTHER volumes.  Segments that
+// come near it are marched step by step with the reference's priority pick over all volumes (K.cu:458-547); the
+// caller has established that the shared label cache never serves foreign labels on this tile (see march_multi_kernel).
+template <int NM, int KTEX, bool MULTI>
+__device__ __forceinline__ void march_core(const VolDev& vol, const float step, const float sx, const float sy, const float sz, const float dx,
+                                           const float dy, const float dz, const float lo, const float hi, float alpha, const int num_steps,
+                                           float4* s_coef, uint8_t* s_code, int lane, float* acc, const MarchParams* MP = nullptr,
+                                           const ViewDev* mvw = nullptr, int udx = 0, int vdx = 0, float olo = 1.0f, float ohi = -1.0f) {
     constexpr bool USE_TEX = KTEX > 0;      // general / slow samples go through the texture unit when there is one
     constexpr bool STAGE_COEF = KTEX < 8;
-    const VolDev& vol = P.vol[0];
-    const float step = P.step;
 #pragma unroll
     for (int m = 0; m < NM; m++) acc[m] = 0.0f;
-
-    // ---- per-lane ray set-up (K.cu:220-334) ----------------------------------------------------
-    float dx = 0.f, dy = 0.f, dz = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f;
-    const float sx = vw.src[0][0], sy = vw.src[0][1], sz = vw.src[0][2];
-    int num_steps = 0;
-    if (pixel_ok && P.enabled[0] != 0) {
-        Ray r = make_ray(vw.w2i, udx, vdx);
-        ray_dir_ijk(r, vw.ijk[0], dx, dy, dz);
-        if (slab_test(dx, dy, dz, sx, sy, sz, vol.ni, vol.nj, vol.nk, P.max_ray_length, lo, hi)) {
-            float minAlpha = fminf(r.ray_length, lo), maxAlpha = fmaxf(0.0f, hi);         // K.cu:242-244, 321-322
-            num_steps = (int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), step));        // K.cu:334
-            num_steps = max(num_steps, 0);
-            alpha = minAlpha;
-        }
-    }
-    my_steps += (unsigned)num_steps;
     const int last = num_steps - 1;
     const int t_end = __reduce_max_sync(0xffffffffu, num_steps);
     if (t_end == 0) return;
@@ -111,9 +99,13 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
     {
         int n0 = 0x7fffffff;
         if (num_steps > 0) {
-            float drift = (float)num_steps * 0x1p-24f * fmaxf(hi, 1.0f);
-            n0 = max(0, (int)floorf(__fdiv_rn(__fsub_rn(__fsub_rn(lo, alpha), drift), step)) - 2);
+            float drift = (float)num_steps * 0x1p-24f * fmaxf(MULTI ? fmaxf(hi, ohi) : hi, 1.0f);
+            n0 = max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(lo, alpha), drift), step), 2.0e9f)) - 2);
             n0 = min(n0, num_steps);
+            if (MULTI) {
+                if (lo > hi) n0 = num_steps;  // this ray never enters the volume
+                if (olo <= ohi) n0 = min(n0, max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(olo, alpha), drift), step), 2.0e9f)) - 2));
+            }
         }
         const int n_skip = __reduce_min_sync(0xffffffffu, n0);
         for (; t < n_skip; t++) alpha = __fadd_rn(alpha, step);
@@ -124,6 +116,53 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
     const int nxm = vol.ni - 2, nym = vol.nj - 2, nzm = vol.nk - 2;  // max cell base
 
     while (t < t_end) {
+        // the march goes on to the far end of the farthest volume (K.cu:321-334); past this volume's window nothing is added
+        if (MULTI) {
+            if (__all_sync(0xffffffffu, t >= num_steps || (alpha > hi + 0.01f && (olo > ohi || alpha > ohi + 0.01f)))) break;
+            const int S0 = min(STAGE_COEF ? SEG_ALU : SEG_TEX, t_end - t);
+            const float a1 = __fmaf_rn((float)S0, step, alpha);
+            const bool near_other = (t < num_steps) && (olo <= ohi) && !(a1 < olo - 0.01f) && !(alpha > ohi + 0.01f);
+            if (__any_sync(0xffffffffu, near_other)) {
+                // ---- mixed segment: priority pick over every volume, sample by sample ----------------
+                w_checkin<NM>(cur, live, acc);
+                const MarchParams& P = *MP;
+                const int V = P.V;
+                const Ray r = make_ray(mvw->w2i, udx, vdx);
+                float dxs[MULTI_MAXV], dys[MULTI_MAXV], dzs[MULTI_MAXV], los[MULTI_MAXV], his[MULTI_MAXV];
+#pragma unroll
+                for (int i = 0; i < MULTI_MAXV; i++) {
+                    dxs[i] = dys[i] = dzs[i] = 0.0f; los[i] = 1.0f; his[i] = -1.0f;  // empty window: never picked
+                    if (i >= V || P.enabled[i] == 0) continue;
+                    ray_dir_ijk(r, mvw->ijk[i], dxs[i], dys[i], dzs[i]);
+                    float lo_i, hi_i;
+                    if (slab_test(dxs[i], dys[i], dzs[i], mvw->src[i][0], mvw->src[i][1], mvw->src[i][2], P.vol[i].ni, P.vol[i].nj, P.vol[i].nk,
+                                  P.max_ray_length, lo_i, hi_i)) { los[i] = lo_i; his[i] = hi_i; }
+                }
+                for (int s = 0; s < S0; s++, t++) {
+                    if (t < num_steps) {
+                        int curr_priority = 0x7fffffff, n_at = 0;  // K.cu:458-496; priorities are distinct here (drr_capi.cu)
+#pragma unroll
+                        for (int i = 0; i < MULTI_MAXV; i++) {
+                            if (alpha < los[i] || alpha > his[i]) continue;
+                            if (P.priority[i] < curr_priority) { curr_priority = P.priority[i]; n_at = 1; }
+                            else if (P.priority[i] == curr_priority) n_at += 1;
+                        }
+                        if (n_at > 0) {
+                            const float weight = __fmul_rn(__fdiv_rn(1.0f, (float)n_at), (t == 0 || t == last) ? 0.5f : 1.0f);  // K.cu:530-537
+#pragma unroll
+                            for (int i = 0; i < MULTI_MAXV; i++) {
+                                if (alpha < los[i] || alpha > his[i] || P.priority[i] != curr_priority) continue;
+                                const float x = __fmaf_rn(alpha, dxs[i], mvw->src[i][0]), y = __fmaf_rn(alpha, dys[i], mvw->src[i][1]),
+                                            z = __fmaf_rn(alpha, dzs[i], mvw->src[i][2]);
+                                w_slow_sample<NM, USE_TEX>(P.vol[i], x, y, z, weight, acc);
+                            }
+                        }
+                    }
+                    alpha = __fadd_rn(alpha, step);  // K.cu:552
+                }
+                continue;
+            }
+        }
         // ---- 1. bound the cells of this segment ------------------------------------------------
         int S = min(STAGE_COEF ? SEG_ALU : SEG_TEX, t_end - t);
         const int cap = STAGE_COEF ? MAXC : MAXC_TEX;
@@ -321,6 +360,28 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
     w_checkin<NM>(cur, live, acc);
 }
 
+// Single-volume tile: per-lane ray set-up (K.cu:220-334), then the lock-step march.
+template <int NM, int KTEX>
+__device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
+                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps) {
+    const VolDev& vol = P.vol[0];
+    float dx = 0.f, dy = 0.f, dz = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f;
+    const float sx = vw.src[0][0], sy = vw.src[0][1], sz = vw.src[0][2];
+    int num_steps = 0;
+    if (pixel_ok && P.enabled[0] != 0) {
+        Ray r = make_ray(vw.w2i, udx, vdx);
+        ray_dir_ijk(r, vw.ijk[0], dx, dy, dz);
+        if (slab_test(dx, dy, dz, sx, sy, sz, vol.ni, vol.nj, vol.nk, P.max_ray_length, lo, hi)) {
+            float minAlpha = fminf(r.ray_length, lo), maxAlpha = fmaxf(0.0f, hi);         // K.cu:242-244, 321-322
+            num_steps = (int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), P.step));  // K.cu:334
+            num_steps = max(num_steps, 0);
+            alpha = minAlpha;
+        }
+    }
+    my_steps += (unsigned)num_steps;
+    march_core<NM, KTEX, false>(vol, P.step, sx, sy, sz, dx, dy, dz, lo, hi, alpha, num_steps, s_coef, s_code, lane, acc);
+}
+
 template <int NM>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_kernel(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -365,6 +426,162 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
     }
     for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
     if (lane == 0 && my_steps) atomicAdd(P.sample_count, my_steps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-volume scenes (BASELINE C3: a CT plus tool volumes).  Along most of every ray only one volume can be picked,
+// and there the march is the single-volume one above -- provided the reference's shared label cache (K.cu:394-396,
+// 416-431) never hands a volume another volume's labels.  With the volumes visited in index order every
+// step, volume i can only start hitting the cache on foreign labels at a step where floor(p_i(t)) equals floor(p_j(t))
+// for a j < i or floor(p_j(t-1)) for a j > i; both sides are straight lines in alpha, so "their difference stays
+// outside the unit cube for the whole march" is a closed-form per-ray test.  A tile that passes it marches its longest
+// volume in lock step and switches to per-sample priority picking (march_core, MULTI) wherever another volume's window
+// is near; a tile that fails goes on a work list for march_general_list_kernel, which replays the reference step by step.
+template <int NM>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_kernel(const __grid_constant__ MarchParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
+    uint8_t* s_code_alu = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
+    uint8_t* s_code_tex = smem_raw + (size_t)warp * WARP_SMEM;
+    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+    const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
+    const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
+    const size_t npix = (size_t)P.W * P.H;
+    const float step = P.step;
+    const int V = P.V;
+    unsigned long long my_steps = 0;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const unsigned view = tile / tiles_per_view;
+        const unsigned tv = tile - view * tiles_per_view;
+        const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
+        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
+        const bool ok = udx < P.W && vdx < P.H;
+        const ViewDev& vw = P.views[view];
+
+        // ---- every volume's slab test, as K.cu:265-334 ---------------------------------------------
+        const Ray r = make_ray(vw.w2i, min(udx, P.W - 1), min(vdx, P.H - 1));
+        float minAlpha = r.ray_length, maxAlpha = 0.0f;
+        float dxs[MULTI_MAXV], dys[MULTI_MAXV], dzs[MULTI_MAXV], los[MULTI_MAXV], his[MULTI_MAXV];
+        unsigned active = 0;  // bit i: this ray has a non-empty window in volume i
+#pragma unroll
+        for (int i = 0; i < MULTI_MAXV; i++) {
+            dxs[i] = dys[i] = dzs[i] = 0.0f; los[i] = 1.0f; his[i] = -1.0f;
+            if (i >= V || P.enabled[i] == 0) continue;
+            ray_dir_ijk(r, vw.ijk[i], dxs[i], dys[i], dzs[i]);
+            float lo_i, hi_i;
+            if (slab_test(dxs[i], dys[i], dzs[i], vw.src[i][0], vw.src[i][1], vw.src[i][2], P.vol[i].ni, P.vol[i].nj, P.vol[i].nk,
+                          P.max_ray_length, lo_i, hi_i)) {
+                minAlpha = fminf(minAlpha, lo_i);
+                maxAlpha = fmaxf(maxAlpha, hi_i);
+                los[i] = lo_i; his[i] = hi_i;
+                if (lo_i <= hi_i) active |= 1u << i;
+            }
+        }
+        int num_steps = max((int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), step)), 0);
+        if (!ok) { num_steps = 0; active = 0; }
+        const unsigned tile_active = __reduce_or_sync(0xffffffffu, active);
+        // Q3 test for every ordered pair (i contributes, j holds the cache): |p_i(alpha) - p_j(alpha - shift)| stays
+        // outside the unit cube on [minAlpha, maxAlpha]
+        bool suspect = false;
+#pragma unroll
+        for (int i = 0; i < MULTI_MAXV; i++) {
+            if (!((active >> i) & 1u)) continue;
+#pragma unroll
+            for (int j = 0; j < MULTI_MAXV; j++) {
+                if (j >= V || j == i) continue;
+                const float shift = j > i ? step : 0.0f;  // volumes after i were last seen one step earlier
+                const float di[3] = {dxs[i], dys[i], dzs[i]}, dj[3] = {dxs[j], dys[j], dzs[j]};
+                float w_lo = minAlpha - 1.0f, w_hi = maxAlpha + 1.0f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float A = (vw.src[i][c] - vw.src[j][c]) + shift * dj[c], B = di[c] - dj[c];
+                    if (B != 0.0f) {
+                        const float a0 = (-1.05f - A) / B, a1 = (1.05f - A) / B;
+                        w_lo = fmaxf(w_lo, fminf(a0, a1));
+                        w_hi = fminf(w_hi, fmaxf(a0, a1));
+                    } else if (fabsf(A) >= 1.05f) {
+                        w_hi = -INFINITY;
+                    }
+                }
+                suspect = suspect || (w_lo <= w_hi);
+            }
+        }
+        if (__any_sync(0xffffffffu, suspect && num_steps > 0)) {
+            if (lane == 0) P.worklist[atomicAdd(P.work_count, 1u)] = tile;
+            continue;
+        }
+        float acc[NM];
+        my_steps += (unsigned long long)num_steps * (unsigned)V;
+        if (tile_active == 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) acc[m] = 0.0f;
+        } else {
+            // the volume marched in lock step: the one with the longest window on this tile
+            int a = 0;
+            unsigned best = 0;
+#pragma unroll
+            for (int i = 0; i < MULTI_MAXV; i++) {
+                const float len = ((active >> i) & 1u) ? fmaxf(his[i] - los[i], 0.0f) + 1.0f : 0.0f;
+                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(len));
+                if (m > best) { best = m; a = i; }
+            }
+            float dx = 0.f, dy = 0.f, dz = 0.f, lo = 1.f, hi = -1.f, olo = INFINITY, ohi = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < MULTI_MAXV; i++) {
+                if (i == a) { dx = dxs[i]; dy = dys[i]; dz = dzs[i]; lo = los[i]; hi = his[i]; }
+                else if ((active >> i) & 1u) { olo = fminf(olo, los[i]); ohi = fmaxf(ohi, his[i]); }
+            }
+            const VolDev& vol = P.vol[a];
+            const float sx = vw.src[a][0], sy = vw.src[a][1], sz = vw.src[a][2];
+            const int cu = min(udx, P.W - 1), cv = min(vdx, P.H - 1);
+            if (P.tex_eighths <= 0)
+                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi);
+            else if (P.tex_eighths >= 8)
+                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, &vw, cu, cv, olo, ohi);
+            else
+                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi);
+        }
+        if (ok) {
+            float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
+#pragma unroll
+            for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[m], step), 10.0f);  // K.cu:565-567, 582-584
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd(P.sample_count, my_steps);
+}
+
+template <int NM>
+static cudaError_t launch_multi_nm(const MarchParams& P, int n_sm, cudaStream_t s) {
+    const size_t smem = (size_t)WARP_SMEM * WARPS_PER_BLOCK;
+    cudaError_t e = cudaFuncSetAttribute(march_multi_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_multi_kernel<NM>, 32 * WARPS_PER_BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    march_multi_kernel<NM><<<n_sm * occ, 32 * WARPS_PER_BLOCK, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t drr_launch_march_multi(const MarchParams& P, int n_sm, cudaStream_t s) {
+    if (P.V > MULTI_MAXV) return cudaErrorInvalidValue;
+    switch (P.M) {
+        case 1: return launch_multi_nm<1>(P, n_sm, s);
+        case 2: return launch_multi_nm<2>(P, n_sm, s);
+        case 3: return launch_multi_nm<3>(P, n_sm, s);
+        case 4: return launch_multi_nm<4>(P, n_sm, s);
+        case 5: return launch_multi_nm<5>(P, n_sm, s);
+        case 6: return launch_multi_nm<6>(P, n_sm, s);
+        case 7: return launch_multi_nm<7>(P, n_sm, s);
+        case 8: return launch_multi_nm<8>(P, n_sm, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

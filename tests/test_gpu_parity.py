@@ -130,6 +130,47 @@ def test_live_reference_kernel_on_new_poses():
     ref.close(); refp.close()
 
 
+@pytest.mark.parametrize("priorities,enabled", [(None, (1, 1, 1)), ([0, 1, 2], (1, 1, 1)), ([2, 0, 1], (1, 0, 1))])
+def test_live_reference_kernel_ct_plus_two_tool_volumes(priorities, enabled):
+    """BASELINE config 3 in small: CT + two crossing K-wire volumes, every sampler, against the reference cubin run on the
+    same poses.  Tiles that see one volume take the lock-step kernel, tiles over the wires its per-sample priority pick,
+    and tiles the shared-label-cache test flags are replayed by the general kernel -- all three must agree with the
+    reference, whatever the priorities, and with a volume switched off."""
+    from oracle import ref_gpu
+
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not shipped")
+    volumes = phantoms.c3_scene((128, 128, 100), (3.2, 3.2, 4.0))
+    for v, e in zip(volumes, enabled):
+        v.enabled = bool(e)
+    poses, sdd = phantoms.cone_poses(2, seed=5, sensor=160, pixel=0.6)
+    k = poses[0].intrinsic
+    st = cases.tables(volumes, "90KV_AL40", priorities)
+    ref = ref_gpu.RefProjector([v.data for v in volumes], st.labels, st.M, lineint=True)
+    pr = priorities if priorities is not None else [2, 1, 0]
+    results = {}
+    for sampler in ("alu", "tex", "hybrid"):
+        with Projector(volumes, priorities=priorities, spectrum="90KV_AL40", neglog=False, camera_intrinsics=k,
+                       source_to_detector_distance=sdd, sampler=sampler) as p:
+            results[sampler] = p.project_line_integrals(*poses)
+            mrl = p.max_ray_length
+    for n, pose in enumerate(poses):
+        w2i, src, ijk = geo.pose_arrays(pose, volumes)
+        li = ref.line_integrals(160, 160, 0.1, w2i, src, ijk, mrl, priority=pr, enabled=list(enabled))
+        iron = st.all_materials.index("iron")
+        if any(enabled[w] and pr[w] < pr[0] for w in (1, 2)):
+            assert (li[iron] > 0).sum() > 100, "a wire that outranks the CT must show up"
+        else:
+            assert not (li[iron] > 0).any()
+        for sampler, area in results.items():
+            for m in range(st.M):
+                mask = li[m] > 0
+                if mask.any():
+                    assert cases.rel_err(area[n, m], li[m])[mask].max() <= LINE_RTOL, (sampler, n, m)
+                assert np.all(area[n, m][~mask] == 0), (sampler, n, m)
+    ref.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # properties and edge cases
 # ---------------------------------------------------------------------------------------------
