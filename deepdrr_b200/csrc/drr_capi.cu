@@ -38,17 +38,20 @@ cudaError_t drr_launch_mesh_transform(const float* verts_local, const int* prim_
                                       int n_views, float* verts_world, cudaStream_t s);
 cudaError_t drr_launch_mesh_subtractive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
                                         int n_prims, int n_tris, int layer, int n_layers, int W, int H, int n_views, int max_hits,
-                                        float far_limit, float* hit_alphas, int8_t* hit_facing, cudaStream_t s);
+                                        float far_limit, float* hit_alphas, int8_t* hit_facing, const int4* tri_box, const int* prim_box,
+                                        cudaStream_t s);
 cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
                                      int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int n_views, int max_hits,
                                      const int8_t* layer_valid, const float* hit_alphas, const int8_t* hit_facing, float* additive,
-                                     cudaStream_t s);
+                                     const int4* tri_box, const int* prim_box, cudaStream_t s);
+cudaError_t drr_launch_mesh_project(const ViewDev* views, const float* source_world, const float* verts_world, const int* prim_of_tri,
+                                    int n_tris, int n_prims, int n_views, int4* tri_box, int* prim_box, cudaStream_t s);
 cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, float far_limit, cudaStream_t s);
 cudaError_t drr_launch_march_meshonly(const MarchParams& P, cudaStream_t s);
 cudaError_t drr_launch_march_multi(const MarchParams& P, int n_sm, cudaStream_t s);
 cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaStream_t s);
 cudaError_t drr_launch_mesh_cover(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
-                                  int n_prims, int W, int H, uint8_t* out, cudaStream_t s);
+                                  int n_prims, int W, int H, uint8_t* out, const int4* tri_box, const int* prim_box, cudaStream_t s);
 cudaError_t drr_launch_mesh_travel_finish(const float* rg, int npix, float* out, cudaStream_t s);
 
 struct ScatterTables {
@@ -216,6 +219,7 @@ struct drr_ctx {
     int8_t* d_own_hit_facing = nullptr;
     size_t wfm_cap = 0, srcw_cap = 0, vw_cap = 0, oha_cap = 0, ohf_cap = 0, oadd_cap = 0;
     unsigned int* d_worklist = nullptr; size_t worklist_cap = 0;
+    int4* d_tri_box = nullptr; int* d_prim_box = nullptr; size_t tribox_cap = 0, primbox_cap = 0;
     // per-batch scratch (grown on demand)
     ViewDev* d_views = nullptr; ViewDev* h_views = nullptr; int views_cap = 0;
     float *d_area = nullptr, *d_intensity = nullptr, *d_pprob = nullptr, *d_scratch = nullptr;
@@ -238,6 +242,17 @@ static int fail(drr_ctx* c, int code, const char* fmt, ...) {
     va_end(ap);
     if (c) c->err = buf; else g_create_err = buf;
     return code;
+}
+
+// 3x3 inverse (double) of world_from_index: maps a world vector from the source to its homogeneous pixel.
+static void invert3(const float* m, float* out) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    const double r = det != 0.0 ? 1.0 / det : 0.0;
+    out[0] = (float)(A * r); out[1] = (float)(-(b * i - c * h) * r); out[2] = (float)((b * f - c * e) * r);
+    out[3] = (float)(B * r); out[4] = (float)((a * i - c * g) * r);  out[5] = (float)(-(a * f - c * d) * r);
+    out[6] = (float)(C * r); out[7] = (float)(-(a * h - b * g) * r); out[8] = (float)((a * e - b * d) * r);
 }
 
 extern "C" {
@@ -309,7 +324,7 @@ int drr_destroy(drr_ctx* c) {
     for (void* p : c->sc_owned) cudaFree(p);
     cudaFree(c->d_sc_cdf); cudaFree(c->d_sc_tally); cudaFree(c->d_sc_counters);
     cudaFree(c->d_verts_local); cudaFree(c->d_prim_of_tri); cudaFree(c->d_prims); cudaFree(c->d_own_mesh_mats); cudaFree(c->d_own_layer_valid);
-    cudaFree(c->d_worklist);
+    cudaFree(c->d_worklist); cudaFree(c->d_tri_box); cudaFree(c->d_prim_box);
     cudaFree(c->d_world_from_mesh); cudaFree(c->d_source_world); cudaFree(c->d_verts_world); cudaFree(c->d_own_hit_alphas);
     cudaFree(c->d_own_additive); cudaFree(c->d_own_hit_facing);
     cudaFree(c->d_energies); cudaFree(c->d_pdf); cudaFree(c->d_mu);
@@ -688,9 +703,9 @@ int drr_mesh_query(drr_ctx* c, int mode, int W, int H, const float* w2i, const u
     const size_t out_bytes = mode == DRR_MESH_QUERY_HITS ? npix * MH * 4 : (mode == DRR_MESH_QUERY_TRAVEL ? npix * 4 : npix);
     const size_t scratch_bytes = mode == DRR_MESH_QUERY_HITS ? npix * MH : (mode == DRR_MESH_QUERY_TRAVEL ? npix * 8 : 0);
     MeshPrimDev* d_prims = nullptr; ViewDev* d_view = nullptr; float *d_wfm = nullptr, *d_src = nullptr, *d_vw = nullptr;
-    void *d_out = nullptr, *d_scratch = nullptr; int8_t* d_valid = nullptr;
+    void *d_out = nullptr, *d_scratch = nullptr; int8_t* d_valid = nullptr; int4* d_tbox = nullptr; int* d_pbox = nullptr;
     int rc = DRR_OK;
-    ViewDev hv; memset(&hv, 0, sizeof hv); memcpy(hv.w2i, w2i, 36);
+    ViewDev hv; memset(&hv, 0, sizeof hv); memcpy(hv.w2i, w2i, 36); invert3(hv.w2i, hv.w2i_inv);
 #define QCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, DRR_E_CUDA, "drr_mesh_query: %s", cudaGetErrorString(e_)); goto done; } } while (0)
     QCU(cudaMalloc(&d_prims, sizeof(MeshPrimDev) * np));
     QCU(cudaMalloc(&d_view, sizeof(ViewDev)));
@@ -698,6 +713,8 @@ int drr_mesh_query(drr_ctx* c, int mode, int W, int H, const float* w2i, const u
     QCU(cudaMalloc(&d_src, 12));
     QCU(cudaMalloc(&d_vw, sizeof(float) * 9 * (size_t)c->n_tris));
     QCU(cudaMalloc(&d_valid, 1));
+    QCU(cudaMalloc(&d_tbox, sizeof(int4) * (size_t)(c->n_tris > 0 ? c->n_tris : 1)));
+    QCU(cudaMalloc(&d_pbox, sizeof(int) * 4 * np));
     if (scratch_bytes) QCU(cudaMalloc(&d_scratch, scratch_bytes));
     if (mem_kind == DRR_MEM_HOST) QCU(cudaMalloc(&d_out, out_bytes)); else d_out = out;
     QCU(cudaMemcpyAsync(d_prims, prims.data(), sizeof(MeshPrimDev) * np, cudaMemcpyHostToDevice, s));
@@ -706,18 +723,20 @@ int drr_mesh_query(drr_ctx* c, int mode, int W, int H, const float* w2i, const u
     QCU(cudaMemcpyAsync(d_src, c->h_source_world.data(), 12, cudaMemcpyHostToDevice, s));
     QCU(cudaMemsetAsync(d_valid, 0, 1, s));
     QCU(drr_launch_mesh_transform(c->d_verts_local, c->d_prim_of_tri, d_wfm, c->n_tris, np, 1, d_vw, s));
-    c->launches += 1;
+    QCU(drr_launch_mesh_project(d_view, d_src, d_vw, c->d_prim_of_tri, c->n_tris, np, 1, d_tbox, d_pbox, s));
+    c->launches += 3;
     if (mode == DRR_MESH_QUERY_HITS) {
         QCU(drr_launch_mesh_subtractive(d_view, d_src, d_vw, d_prims, np, c->n_tris, 0, 1, W, H, 1, MH, c->far_limit, (float*)d_out,
-                                        (int8_t*)d_scratch, s));
+                                        (int8_t*)d_scratch, d_tbox, d_pbox, s));
         c->launches += 1;
     } else if (mode == DRR_MESH_QUERY_TRAVEL) {
         QCU(cudaMemsetAsync(d_scratch, 0, scratch_bytes, s));
-        QCU(drr_launch_mesh_additive(d_view, d_src, d_vw, d_prims, np, c->n_tris, 1, 1, W, H, 1, MH, d_valid, nullptr, nullptr, (float*)d_scratch, s));
+        QCU(drr_launch_mesh_additive(d_view, d_src, d_vw, d_prims, np, c->n_tris, 1, 1, W, H, 1, MH, d_valid, nullptr, nullptr, (float*)d_scratch,
+                                     d_tbox, d_pbox, s));
         QCU(drr_launch_mesh_travel_finish((const float*)d_scratch, (int)npix, (float*)d_out, s));
         c->launches += 2;
     } else {
-        QCU(drr_launch_mesh_cover(d_view, d_src, d_vw, d_prims, np, W, H, (uint8_t*)d_out, s));
+        QCU(drr_launch_mesh_cover(d_view, d_src, d_vw, d_prims, np, W, H, (uint8_t*)d_out, d_tbox, d_pbox, s));
         c->launches += 1;
     }
     if (mem_kind == DRR_MEM_HOST) QCU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
@@ -725,6 +744,7 @@ int drr_mesh_query(drr_ctx* c, int mode, int W, int H, const float* w2i, const u
 #undef QCU
 done:
     cudaFree(d_prims); cudaFree(d_view); cudaFree(d_wfm); cudaFree(d_src); cudaFree(d_vw); cudaFree(d_valid); cudaFree(d_scratch);
+    cudaFree(d_tbox); cudaFree(d_pbox);
     if (mem_kind == DRR_MEM_HOST) cudaFree(d_out);
     return rc;
 }
@@ -809,6 +829,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         ViewDev& vd = c->h_views[i];
         memset(&vd, 0, sizeof vd);
         memcpy(vd.w2i, w2i + (size_t)i * 9, 36);
+        invert3(vd.w2i, vd.w2i_inv);
         for (int v = 0; v < V; v++) {
             memcpy(vd.src[v], src_ijk + ((size_t)i * V + v) * 3, 12);
             memcpy(vd.ijk[v], ijk_from_world + ((size_t)i * V + v) * 12, 48);
@@ -855,16 +876,21 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         CU(c, cudaMemcpyAsync(c->d_source_world, c->h_source_world.data(), sizeof(float) * 3 * (size_t)n_views, cudaMemcpyHostToDevice, s));
         CU(c, cudaMemsetAsync(c->d_own_hit_facing, 0, (size_t)n_views * L * npix * MH, s));
         CU(c, cudaMemsetAsync(c->d_own_additive, 0, sizeof(float) * 2 * (size_t)n_views * L * NMm * npix, s));
+        if ((rc = ensure(c, (void**)&c->d_tri_box, &c->tribox_cap, sizeof(int4) * (size_t)n_views * (c->n_tris > 0 ? c->n_tris : 1)))) return rc;
+        if ((rc = ensure(c, (void**)&c->d_prim_box, &c->primbox_cap, sizeof(int) * 4 * (size_t)n_views * c->n_prims))) return rc;
         CU(c, drr_launch_mesh_transform(c->d_verts_local, c->d_prim_of_tri, c->d_world_from_mesh, c->n_tris, c->n_prims, n_views, c->d_verts_world, s));
-        c->launches += 1;
+        CU(c, drr_launch_mesh_project(c->d_views, c->d_source_world, c->d_verts_world, c->d_prim_of_tri, c->n_tris, c->n_prims, n_views,
+                                      c->d_tri_box, c->d_prim_box, s));
+        c->launches += 3;
         for (int l = L - 1; l >= 0; l--) {
             if (!c->h_layer_valid[l]) continue;
             CU(c, drr_launch_mesh_subtractive(c->d_views, c->d_source_world, c->d_verts_world, c->d_prims, c->n_prims, c->n_tris, l, L, W, H, n_views,
-                                              MH, c->far_limit, c->d_own_hit_alphas, c->d_own_hit_facing, s));
+                                              MH, c->far_limit, c->d_own_hit_alphas, c->d_own_hit_facing, c->d_tri_box, c->d_prim_box, s));
             c->launches += 1;
         }
         CU(c, drr_launch_mesh_additive(c->d_views, c->d_source_world, c->d_verts_world, c->d_prims, c->n_prims, c->n_tris, L, NMm, W, H, n_views, MH,
-                                       c->d_own_layer_valid, c->d_own_hit_alphas, c->d_own_hit_facing, c->d_own_additive, s));
+                                       c->d_own_layer_valid, c->d_own_hit_alphas, c->d_own_hit_facing, c->d_own_additive, c->d_tri_box,
+                                       c->d_prim_box, s));
         c->launches += 1;
         P.mesh_layers = L; P.max_hits = MH; P.n_mesh_mats = NMm;
         P.hit_alphas = c->d_own_hit_alphas; P.hit_facing = c->d_own_hit_facing; P.layer_valid = c->d_own_layer_valid;
@@ -898,7 +924,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         for (int v = 0; v < V; v++)
             if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_project: volume %d has no raw arrays", v);
         // Tiles whose rays see a single volume take the lock-step kernel; the others are listed for the general one.
-        bool split = V > 1 && !meshes && !c->attenuate_outside && c->variant == 0;
+        bool split = !c->attenuate_outside && c->variant == 0;  // (V == 1 gets here only with meshes)
         int sampler = c->sampler;
         for (int v = 0; v < V && split; v++) {
             const VolHost& h = c->vols[v];

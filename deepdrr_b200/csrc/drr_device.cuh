@@ -30,6 +30,7 @@ struct ViewDev {  // per-view inputs, projector.py:802-831
     float w2i[9];
     float src[DRR_MAX_VOLUMES][3];
     float ijk[DRR_MAX_VOLUMES][12];
+    float w2i_inv[9];  // inverse of w2i: world vector -> homogeneous pixel (mesh binning only)
 };
 
 struct MarchParams {

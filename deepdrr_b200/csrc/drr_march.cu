@@ -489,6 +489,7 @@ static cudaError_t launch_general_list_nv(const MarchParams& P, int grid, cudaSt
 
 cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaStream_t s) {
     switch (P.V) {
+        case 1: return launch_general_list_nv<1>(P, grid, s);
         case 2: return launch_general_list_nv<2>(P, grid, s);
         case 3: return launch_general_list_nv<3>(P, grid, s);
         case 4: return launch_general_list_nv<4>(P, grid, s);

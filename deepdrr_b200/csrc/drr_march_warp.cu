@@ -83,7 +83,7 @@ template <int NM, int KTEX, bool MULTI>
 __device__ __forceinline__ void march_core(const VolDev& vol, const float step, const float sx, const float sy, const float sz, const float dx,
                                            const float dy, const float dz, const float lo, const float hi, float alpha, const int num_steps,
                                            float4* s_coef, uint8_t* s_code, int lane, float* acc, const MarchParams* MP = nullptr,
-                                           const ViewDev* mvw = nullptr, int udx = 0, int vdx = 0, float olo = 1.0f, float ohi = -1.0f) {
+                                           const ViewDev* mvw = nullptr, int udx = 0, int vdx = 0, float olo = 1.0f, float ohi = -1.0f, int view = 0) {
     constexpr bool USE_TEX = KTEX > 0;      // general / slow samples go through the texture unit when there is one
     constexpr bool STAGE_COEF = KTEX < 8;
 #pragma unroll
@@ -138,8 +138,25 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                     if (slab_test(dxs[i], dys[i], dzs[i], mvw->src[i][0], mvw->src[i][1], mvw->src[i][2], P.vol[i].ni, P.vol[i].nj, P.vol[i].nk,
                                   P.max_ray_length, lo_i, hi_i)) { los[i] = lo_i; his[i] = hi_i; }
                 }
+                // subtractive meshes (K.cu:498-517): the depth counters are a function of alpha alone, so they are
+                // rebuilt here from the head of each hit list and advanced step by step
+                const bool carve = P.layer_valid != nullptr;
+                int hidx[4] = {0, 0, 0, 0}, hdep[4] = {0, 0, 0, 0};
+                const size_t npix = (size_t)P.W * P.H;
+                const size_t hbase = (((size_t)view * P.mesh_layers) * npix + (size_t)vdx * P.W + udx) * P.max_hits;
                 for (int s = 0; s < S0; s++, t++) {
-                    if (t < num_steps) {
+                    bool inside_mesh = false;
+                    if (carve) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (j >= P.mesh_layers || P.layer_valid[j] == 0) continue;
+                            const float* ha = P.hit_alphas + hbase + (size_t)j * npix * P.max_hits;
+                            const int8_t* hf = P.hit_facing + hbase + (size_t)j * npix * P.max_hits;
+                            while (hidx[j] < P.max_hits && hf[hidx[j]] != 0 && ha[hidx[j]] < alpha) { hdep[j] += hf[hidx[j]]; hidx[j] += 1; }
+                            if (hdep[j] > 0) inside_mesh = true;
+                        }
+                    }
+                    if (t < num_steps && !inside_mesh) {
                         int curr_priority = 0x7fffffff, n_at = 0;  // K.cu:458-496; priorities are distinct here (drr_capi.cu)
 #pragma unroll
                         for (int i = 0; i < MULTI_MAXV; i++) {
@@ -511,6 +528,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_
                 suspect = suspect || (w_lo <= w_hi);
             }
         }
+        // where this ray can be inside a subtractive mesh (K.cu:498-517): from its first hit to its last one, or to the
+        // end of the march if the entries and exits of a layer do not balance
+        float mesh_lo = INFINITY, mesh_hi = -INFINITY;
+        if (P.layer_valid != nullptr && ok) {
+            const size_t pix = (size_t)vdx * P.W + udx;
+            for (int j = 0; j < P.mesh_layers; j++) {
+                if (P.layer_valid[j] == 0) continue;
+                const float* ha = P.hit_alphas + (((size_t)view * P.mesh_layers + j) * npix + pix) * P.max_hits;
+                const int8_t* hf = P.hit_facing + (((size_t)view * P.mesh_layers + j) * npix + pix) * P.max_hits;
+                int depth = 0;
+                for (int k = 0; k < P.max_hits && hf[k] != 0; k++) {
+                    mesh_lo = fminf(mesh_lo, ha[k]); mesh_hi = fmaxf(mesh_hi, ha[k]);
+                    depth += hf[k];
+                }
+                if (depth > 0) mesh_hi = INFINITY;
+            }
+        }
         if (__any_sync(0xffffffffu, suspect && num_steps > 0)) {
             if (lane == 0) P.worklist[atomicAdd(P.work_count, 1u)] = tile;
             continue;
@@ -536,20 +570,37 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_
                 if (i == a) { dx = dxs[i]; dy = dys[i]; dz = dzs[i]; lo = los[i]; hi = his[i]; }
                 else if ((active >> i) & 1u) { olo = fminf(olo, los[i]); ohi = fmaxf(ohi, his[i]); }
             }
+            if (mesh_lo <= mesh_hi) { olo = fminf(olo, mesh_lo - 0.05f); ohi = fmaxf(ohi, mesh_hi + 0.05f); }
             const VolDev& vol = P.vol[a];
             const float sx = vw.src[a][0], sy = vw.src[a][1], sz = vw.src[a][2];
             const int cu = min(udx, P.W - 1), cv = min(vdx, P.H - 1);
             if (P.tex_eighths <= 0)
-                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi);
+                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
             else if (P.tex_eighths >= 8)
-                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, &vw, cu, cv, olo, ohi);
+                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
             else
-                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi);
+                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
         }
         if (ok) {
-            float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
+            const size_t pix = (size_t)vdx * P.W + udx;
 #pragma unroll
-            for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[m], step), 10.0f);  // K.cu:565-567, 582-584
+            for (int m = 0; m < NM; m++) acc[m] = __fmul_rn(acc[m], step);  // K.cu:565-567
+            if (P.additive != nullptr) {                                    // K.cu:569-579
+                const float* add = P.additive + (size_t)view * P.mesh_layers * P.n_mesh_mats * npix * 2;
+                for (int i = 0; i < P.n_mesh_mats; i++)
+                    for (int j = 0; j < P.mesh_layers; j++) {
+                        const size_t idx = ((size_t)j * P.n_mesh_mats + i) * npix * 2 + pix * 2;
+                        if (fabs((double)add[idx + 1]) < 0.00001) {
+                            const int mm = P.mesh_mats[i];
+                            const float v = fmaxf(add[idx], 0.0f);
+#pragma unroll
+                            for (int m = 0; m < NM; m++) if (m == mm) acc[m] = __fadd_rn(acc[m], v);
+                        }
+                    }
+            }
+            float* out = P.area + (size_t)view * P.M * npix + pix;
+#pragma unroll
+            for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(acc[m], 10.0f);  // K.cu:582-584
         }
     }
     for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);

@@ -46,6 +46,71 @@ __global__ void mesh_transform_kernel(const float* __restrict__ verts_local, con
     o[2] = M[8] * x + M[9] * y + M[10] * z + M[11];
 }
 
+// Screen-space boxes: all rays leave one point, so a triangle can only be hit by the pixels its projection covers.
+// tri_box[view][tri] = (u_min, u_max, v_min, v_max) in pixel indices with one pixel of slack; triangles with a vertex
+// at or behind the source plane get an unbounded box.  prim_box[view][prim][4] is the union over the primitive.
+#define BOX_INF (1 << 30)
+__global__ void mesh_box_init_kernel(int* __restrict__ prim_box, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) prim_box[i] = (i & 1) ? -BOX_INF : BOX_INF;  // (min, max, min, max)
+}
+
+__global__ void mesh_project_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
+                                    const float* __restrict__ verts_world, const int* __restrict__ prim_of_tri, int n_tris, int n_prims,
+                                    int4* __restrict__ tri_box, int* __restrict__ prim_box) {
+    const int tri = blockIdx.x * blockDim.x + threadIdx.x, view = blockIdx.y;
+    if (tri >= n_tris) return;
+    const float* W = views[view].w2i_inv;
+    const float* v = verts_world + ((size_t)view * n_tris + tri) * 9;
+    const float ox = source_world[3 * view], oy = source_world[3 * view + 1], oz = source_world[3 * view + 2];
+    float umin = 3e9f, umax = -3e9f, vmin = 3e9f, vmax = -3e9f;
+    bool unbounded = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float x = v[3 * k] - ox, y = v[3 * k + 1] - oy, z = v[3 * k + 2] - oz;
+        const float qx = W[0] * x + W[1] * y + W[2] * z, qy = W[3] * x + W[4] * y + W[5] * z, qz = W[6] * x + W[7] * y + W[8] * z;
+        if (!(qz > 1e-6f * (fabsf(qx) + fabsf(qy)) && qz > 0.0f)) { unbounded = true; continue; }
+        const float pu = fminf(fmaxf(qx / qz, -1e9f), 1e9f), pv = fminf(fmaxf(qy / qz, -1e9f), 1e9f);
+        umin = fminf(umin, pu); umax = fmaxf(umax, pu); vmin = fminf(vmin, pv); vmax = fmaxf(vmax, pv);
+    }
+    int4 b;
+    if (unbounded) b = make_int4(-BOX_INF, BOX_INF, -BOX_INF, BOX_INF);
+    else b = make_int4((int)floorf(umin - 1.5f), (int)ceilf(umax + 0.5f), (int)floorf(vmin - 1.5f), (int)ceilf(vmax + 0.5f));
+    tri_box[(size_t)view * n_tris + tri] = b;
+    int* pb = prim_box + ((size_t)view * n_prims + prim_of_tri[tri]) * 4;
+    atomicMin(pb + 0, b.x); atomicMax(pb + 1, b.y); atomicMin(pb + 2, b.z); atomicMax(pb + 3, b.w);
+}
+
+// Stage those triangles of [base, base + cnt) whose box meets the tile [u0, u1] x [v0, v1], in index order (so sums
+// over triangles keep their order).  All 128 threads of the block call it; returns the number staged.
+__device__ __forceinline__ int stage_chunk(const float* __restrict__ vw, const int4* __restrict__ tb, int base, int cnt, int u0, int u1,
+                                           int v0, int v1, float* s_v, int* s_cnt) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool keep = false;
+    if (tid < cnt) {
+        const int4 b = tb[base + tid];
+        keep = b.x <= u1 && b.y >= u0 && b.z <= v1 && b.w >= v0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncthreads();  // the previous chunk has been consumed
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; w++) off += s_cnt[w];
+    const int total = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+    if (keep) {
+        const float* src = vw + (size_t)(base + tid) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; i++) s_v[off * 9 + i] = src[i];
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool prim_misses_tile(const int* __restrict__ pb, int u0, int u1, int v0, int v1) {
+    return pb[0] > u1 || pb[1] < u0 || pb[2] > v1 || pb[3] < v0;
+}
+
 // Moeller-Trumbore, double sided.  Returns true and (t, entering) for t > 0.
 __device__ __forceinline__ bool ray_tri(const float3& o, const float3& d, const float* __restrict__ v, float& t, bool& entering) {
     const float3 e1 = make_float3(v[3] - v[0], v[4] - v[1], v[5] - v[2]);
@@ -126,8 +191,10 @@ __global__ void tide_clean_kernel(float* __restrict__ ts, int8_t* __restrict__ f
 __global__ void __launch_bounds__(128) mesh_subtractive_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
                                                                const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
                                                                int n_prims, int n_tris, int layer, int n_layers, int W, int H, int max_hits,
-                                                               float far_limit, float* __restrict__ hit_alphas, int8_t* __restrict__ hit_facing) {
+                                                               float far_limit, float* __restrict__ hit_alphas, int8_t* __restrict__ hit_facing,
+                                                               const int4* __restrict__ tri_box, const int* __restrict__ prim_box) {
     __shared__ float s_v[MESH_CHUNK * 9];
+    __shared__ int s_cnt[4];
     const int tiles_x = (W + 15) / 16;
     const int view = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -144,11 +211,10 @@ __global__ void __launch_bounds__(128) mesh_subtractive_kernel(const ViewDev* __
     for (int p = 0; p < n_prims; p++) {
         const MeshPrimDev pr = prims[p];
         if (!pr.subtractive || pr.layer != layer) continue;
+        if (prim_misses_tile(prim_box + ((size_t)view * n_prims + p) * 4, tx * 16, tx * 16 + 15, ty * 8, ty * 8 + 7)) continue;
         for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
-            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
-            __syncthreads();
-            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = vw[(size_t)base * 9 + i];
-            __syncthreads();
+            const int cnt = stage_chunk(vw, tri_box + (size_t)view * n_tris, base, min(MESH_CHUNK, pr.tri_end - base), tx * 16, tx * 16 + 15,
+                                        ty * 8, ty * 8 + 7, s_v, s_cnt);
             if (!ok) continue;
             for (int k = 0; k < cnt; k++) {
                 float t; bool entering;
@@ -177,8 +243,10 @@ __global__ void __launch_bounds__(128) mesh_additive_kernel(const ViewDev* __res
                                                             const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
                                                             int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int max_hits,
                                                             const int8_t* __restrict__ layer_valid, const float* __restrict__ hit_alphas,
-                                                            const int8_t* __restrict__ hit_facing, float* __restrict__ additive) {
+                                                            const int8_t* __restrict__ hit_facing, float* __restrict__ additive,
+                                                            const int4* __restrict__ tri_box, const int* __restrict__ prim_box) {
     __shared__ float s_v[MESH_CHUNK * 9];
+    __shared__ int s_cnt[4];
     const int tiles_x = (W + 15) / 16;
     const int view = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -192,13 +260,12 @@ __global__ void __launch_bounds__(128) mesh_additive_kernel(const ViewDev* __res
     for (int p = 0; p < n_prims; p++) {
         const MeshPrimDev pr = prims[p];
         if (!pr.additive || pr.mat_slot < 0 || pr.layer < 0 || pr.layer >= n_layers) continue;
+        if (prim_misses_tile(prim_box + ((size_t)view * n_prims + p) * 4, tx * 16, tx * 16 + 15, ty * 8, ty * 8 + 7)) continue;
         const float rho = fmaxf(pr.density, 0.0f);  // renderer.py:424-425
         float R = 0.0f, G = 0.0f;
         for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
-            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
-            __syncthreads();
-            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = vw[(size_t)base * 9 + i];
-            __syncthreads();
+            const int cnt = stage_chunk(vw, tri_box + (size_t)view * n_tris, base, min(MESH_CHUNK, pr.tri_end - base), tx * 16, tx * 16 + 15,
+                                        ty * 8, ty * 8 + 7, s_v, s_cnt);
             if (!ok) continue;
             for (int k = 0; k < cnt; k++) {
                 float t; bool entering;
@@ -230,8 +297,10 @@ __global__ void __launch_bounds__(128) mesh_additive_kernel(const ViewDev* __res
 // Coverage mask (project_seg): 255 where any triangle of a selected primitive is hit, front or back face.
 __global__ void __launch_bounds__(128) mesh_cover_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
                                                          const float* __restrict__ verts_world, const MeshPrimDev* __restrict__ prims,
-                                                         int n_prims, int W, int H, uint8_t* __restrict__ out) {
+                                                         int n_prims, int W, int H, uint8_t* __restrict__ out,
+                                                         const int4* __restrict__ tri_box, const int* __restrict__ prim_box) {
     __shared__ float s_v[MESH_CHUNK * 9];
+    __shared__ int s_cnt[4];
     const int tiles_x = (W + 15) / 16;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int udx = tx * 16 + (threadIdx.x & 15), vdx = ty * 8 + (threadIdx.x >> 4);
@@ -243,11 +312,10 @@ __global__ void __launch_bounds__(128) mesh_cover_kernel(const ViewDev* __restri
     for (int p = 0; p < n_prims; p++) {
         const MeshPrimDev pr = prims[p];
         if (!pr.subtractive) continue;  // the query marks the selected primitives this way
+        if (prim_misses_tile(prim_box + (size_t)p * 4, tx * 16, tx * 16 + 15, ty * 8, ty * 8 + 7)) continue;
         for (int base = pr.tri_begin; base < pr.tri_end; base += MESH_CHUNK) {
-            const int cnt = min(MESH_CHUNK, pr.tri_end - base);
-            __syncthreads();
-            for (int i = threadIdx.x; i < cnt * 9; i += blockDim.x) s_v[i] = verts_world[(size_t)base * 9 + i];
-            __syncthreads();
+            const int cnt = stage_chunk(verts_world, tri_box, base, min(MESH_CHUNK, pr.tri_end - base), tx * 16, tx * 16 + 15, ty * 8, ty * 8 + 7,
+                                        s_v, s_cnt);
             if (!ok || hit) continue;
             for (int k = 0; k < cnt && !hit; k++) {
                 float t; bool entering;
@@ -278,20 +346,21 @@ cudaError_t drr_launch_mesh_transform(const float* verts_local, const int* prim_
 
 cudaError_t drr_launch_mesh_subtractive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
                                         int n_prims, int n_tris, int layer, int n_layers, int W, int H, int n_views, int max_hits,
-                                        float far_limit, float* hit_alphas, int8_t* hit_facing, cudaStream_t s) {
+                                        float far_limit, float* hit_alphas, int8_t* hit_facing, const int4* tri_box, const int* prim_box,
+                                        cudaStream_t s) {
     dim3 grid(((W + 15) / 16) * ((H + 7) / 8), n_views);
     mesh_subtractive_kernel<<<grid, 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, n_tris, layer, n_layers, W, H, max_hits,
-                                                 far_limit, hit_alphas, hit_facing);
+                                                 far_limit, hit_alphas, hit_facing, tri_box, prim_box);
     return cudaGetLastError();
 }
 
 cudaError_t drr_launch_mesh_additive(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
                                      int n_prims, int n_tris, int n_layers, int n_mats, int W, int H, int n_views, int max_hits,
                                      const int8_t* layer_valid, const float* hit_alphas, const int8_t* hit_facing, float* additive,
-                                     cudaStream_t s) {
+                                     const int4* tri_box, const int* prim_box, cudaStream_t s) {
     dim3 grid(((W + 15) / 16) * ((H + 7) / 8), n_views);
     mesh_additive_kernel<<<grid, 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, n_tris, n_layers, n_mats, W, H, max_hits,
-                                              layer_valid, hit_alphas, hit_facing, additive);
+                                              layer_valid, hit_alphas, hit_facing, additive, tri_box, prim_box);
     return cudaGetLastError();
 }
 
@@ -301,12 +370,25 @@ cudaError_t drr_launch_tide_clean(float* ts, int8_t* facing, int n_rays, int n, 
 }
 
 cudaError_t drr_launch_mesh_cover(const ViewDev* views, const float* source_world, const float* verts_world, const MeshPrimDev* prims,
-                                  int n_prims, int W, int H, uint8_t* out, cudaStream_t s) {
-    mesh_cover_kernel<<<((W + 15) / 16) * ((H + 7) / 8), 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, W, H, out);
+                                  int n_prims, int W, int H, uint8_t* out, const int4* tri_box, const int* prim_box, cudaStream_t s) {
+    mesh_cover_kernel<<<((W + 15) / 16) * ((H + 7) / 8), 128, 0, s>>>(views, source_world, verts_world, prims, n_prims, W, H, out, tri_box,
+                                                                       prim_box);
     return cudaGetLastError();
 }
 
 cudaError_t drr_launch_mesh_travel_finish(const float* rg, int npix, float* out, cudaStream_t s) {
     mesh_travel_finish_kernel<<<(npix + 255) / 256, 256, 0, s>>>(rg, npix, out);
+    return cudaGetLastError();
+}
+
+// Fills tri_box [n_views][n_tris] and prim_box [n_views][n_prims][4] for the transformed vertices.
+cudaError_t drr_launch_mesh_project(const ViewDev* views, const float* source_world, const float* verts_world, const int* prim_of_tri,
+                                    int n_tris, int n_prims, int n_views, int4* tri_box, int* prim_box, cudaStream_t s) {
+    const int n = n_views * n_prims * 4;
+    mesh_box_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(prim_box, n);
+    if (n_tris > 0) {
+        dim3 grid((n_tris + 255) / 256, n_views);
+        mesh_project_kernel<<<grid, 256, 0, s>>>(views, source_world, verts_world, prim_of_tri, n_tris, n_prims, tri_box, prim_box);
+    }
     return cudaGetLastError();
 }
