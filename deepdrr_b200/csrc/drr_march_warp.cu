@@ -40,6 +40,17 @@
 #endif
 #define MULTI_MAXV 4                   // volumes the multi-volume variant handles
 
+// tile id -> view and this lane's pixel (8x4 tiles, row-major per view)
+__device__ __forceinline__ void tile_pixel(const MarchParams& P, unsigned tile, int lane, int& view, int& udx, int& vdx) {
+    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+    const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
+    view = (int)(tile / tiles_per_view);
+    const unsigned tv = tile - (unsigned)view * tiles_per_view;
+    const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
+    udx = tx * TILE_W + (lane & (TILE_W - 1));
+    vdx = ty * TILE_H + (lane >> 3);
+}
+
 // ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
 template <int NM>
 __device__ __forceinline__ void w_checkin(float cur, int& live, float* acc) {
@@ -83,7 +94,7 @@ template <int NM, int KTEX, bool MULTI>
 __device__ __forceinline__ void march_core(const VolDev& vol, const float step, const float sx, const float sy, const float sz, const float dx,
                                            const float dy, const float dz, const float lo, const float hi, float alpha, const int num_steps,
                                            float4* s_coef, uint8_t* s_code, int lane, float* acc, const MarchParams* MP = nullptr,
-                                           const ViewDev* mvw = nullptr, int udx = 0, int vdx = 0, float olo = 1.0f, float ohi = -1.0f, int view = 0) {
+                                           unsigned tile = 0, float olo = 1.0f, float ohi = -1.0f) {
     constexpr bool USE_TEX = KTEX > 0;      // general / slow samples go through the texture unit when there is one
     constexpr bool STAGE_COEF = KTEX < 8;
 #pragma unroll
@@ -127,6 +138,10 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                 w_checkin<NM>(cur, live, acc);
                 const MarchParams& P = *MP;
                 const int V = P.V;
+                int view, udx, vdx;  // recomputed from the tile id rather than kept in registers through the march
+                tile_pixel(P, tile, lane, view, udx, vdx);
+                udx = min(udx, P.W - 1); vdx = min(vdx, P.H - 1);
+                const ViewDev* mvw = P.views + view;
                 const Ray r = make_ray(mvw->w2i, udx, vdx);
                 float dxs[MULTI_MAXV], dys[MULTI_MAXV], dzs[MULTI_MAXV], los[MULTI_MAXV], his[MULTI_MAXV];
 #pragma unroll
@@ -343,35 +358,56 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         }
 
         // ---- 3b. general segment: per-sample label code and range check ----------------------------
-        for (int s = 0; s < S; s++, t++) {
-            const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
-            const bool inr = (t < num_steps) && !(alpha < lo) && !(alpha > hi);  // K.cu:472
-            float rho = 0.0f;
-            if (USE_TEX && inr) rho = tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
-            // cell-local coordinates: l = p - box_lo, p = x - 1 (K.cu:402-404); exact for x >= 1
-            const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-            const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
-            int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
-            idx = inr ? min(max(idx, 0), ncell - 1) : 0;
-            int code = s_code[idx];
-            if ((t == 0) | (t == last)) code = 0xFF;  // half-weighted end samples take the generic path
-            if (inr) {
-                if (code != live) {
-                    w_checkin<NM>(cur, live, acc);
-                    if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
-                }
-                if (code != 0xFF) {
-                    if (USE_TEX) {
-                        cur = __fadd_rn(cur, rho);
-                    } else if (STAGE_COEF) {
-                        const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
-                        cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+        // four steps at a time, so that the texture fetches of a group are in flight together
+        for (int s0 = 0; s0 < S; s0 += 4) {
+            const int nb = min(4, S - s0);
+            float aj[4], rj[4];
+            aj[0] = alpha;
+#pragma unroll
+            for (int j = 1; j < 4; j++) aj[j] = __fadd_rn(aj[j - 1], step);  // K.cu:552
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                rj[j] = 0.0f;
+                if (USE_TEX && j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi))
+                    rj[j] = tex3D<float>(vol.tex, __fsub_rn(__fmaf_rn(aj[j], dx, sx), 0.5f), __fsub_rn(__fmaf_rn(aj[j], dy, sy), 0.5f),
+                                         __fsub_rn(__fmaf_rn(aj[j], dz, sz), 0.5f));  // K.cu:542
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < nb) {
+                    const float a = aj[j];
+                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                    const bool inr = (t < num_steps) && !(a < lo) && !(a > hi);  // K.cu:472
+                    // cell-local coordinates: l = p - box_lo, p = x - 1 (K.cu:402-404); exact for x >= 1
+                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                    int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
+                    idx = inr ? min(max(idx, 0), ncell - 1) : 0;
+                    int code = s_code[idx];
+                    if ((t == 0) | (t == last)) code = 0xFF;  // half-weighted end samples take the generic path
+                    if (inr) {
+                        if (code != live) {
+                            w_checkin<NM>(cur, live, acc);
+                            if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
+                        }
+                        if (code != 0xFF) {
+                            if (USE_TEX) {
+                                cur = __fadd_rn(cur, rj[j]);
+                            } else if (STAGE_COEF) {
+                                const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                                cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                            }
+                        } else {
+                            w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                        }
                     }
-                } else {
-                    w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                    t++;
                 }
             }
-            alpha = __fadd_rn(alpha, step);  // K.cu:552
+            float a_last = aj[0];
+#pragma unroll
+            for (int j = 1; j < 4; j++) a_last = (j < nb) ? aj[j] : a_last;
+            alpha = __fadd_rn(a_last, step);
         }
     }
     w_checkin<NM>(cur, live, acc);
@@ -573,16 +609,18 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_
             if (mesh_lo <= mesh_hi) { olo = fminf(olo, mesh_lo - 0.05f); ohi = fmaxf(ohi, mesh_hi + 0.05f); }
             const VolDev& vol = P.vol[a];
             const float sx = vw.src[a][0], sy = vw.src[a][1], sz = vw.src[a][2];
-            const int cu = min(udx, P.W - 1), cv = min(vdx, P.H - 1);
             if (P.tex_eighths <= 0)
-                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
+                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, tile, olo, ohi);
             else if (P.tex_eighths >= 8)
-                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
+                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, tile, olo, ohi);
             else
-                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, &vw, cu, cv, olo, ohi, (int)view);
+                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, tile, olo, ohi);
         }
-        if (ok) {
-            const size_t pix = (size_t)vdx * P.W + udx;
+        int view2, u2, v2;
+        tile_pixel(P, tile, lane, view2, u2, v2);
+        if (u2 < P.W && v2 < P.H) {
+            const size_t pix = (size_t)v2 * P.W + u2;
+            const int view = view2;
 #pragma unroll
             for (int m = 0; m < NM; m++) acc[m] = __fmul_rn(acc[m], step);  // K.cu:565-567
             if (P.additive != nullptr) {                                    // K.cu:569-579

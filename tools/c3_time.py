@@ -13,6 +13,7 @@ small = "--small" in sys.argv
 vols = phantoms.c3_scene((128, 128, 100), (3.2, 3.2, 4.0)) if small else phantoms.c3_scene()
 poses, sdd = phantoms.cone_poses(n_views)
 with Projector(vols, spectrum="120KV_AL43", step=0.1, neglog=False, camera_intrinsics=poses[0].intrinsic, source_to_detector_distance=sdd) as p:
+    p.project_line_integrals(*poses[:1])  # warm-up (module load, attribute set-up)
     t0 = time.time()
     area = p.project_line_integrals(*poses)
     area = area.reshape((n_views,) + area.shape[-3:])
