@@ -264,10 +264,12 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                     if (e < ncell) {
                         const size_t cell = cell_of(e);
                         cc[k] = __ldg(vol.cellcode + cell);
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_coef + 2 * e);
+                        // the two 16 B halves of a record go to separate planes: consecutive cells then fall into
+                        // distinct 16 B bank groups for the LDS.128 of the FMA-pipe sampler
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_coef + e);
                         const float4* src = vol.cellc + 2 * cell;
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 1));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(MAXC * 16)), "l"(src + 1));
                     }
                 }
                 asm volatile("cp.async.commit_group;");
@@ -317,7 +319,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                 const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
                 const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
                 const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
-                const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
                 return hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB);
             };
             if (KTEX == 8) {
@@ -394,7 +396,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                             if (USE_TEX) {
                                 cur = __fadd_rn(cur, rj[j]);
                             } else if (STAGE_COEF) {
-                                const float4 cA = s_coef[2 * idx], cB = s_coef[2 * idx + 1];
+                                const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
                                 cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
                             }
                         } else {
