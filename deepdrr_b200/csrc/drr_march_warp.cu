@@ -67,7 +67,44 @@ __device__ __forceinline__ float w_checkout(int label, int& live, const float* a
     return cur;
 }
 
-// Generic sample straight from global memory: mixed-label / clamped cells and half-weighted ends.
+// Generic sample straight from global memory: mixed-label / clamped cells and half-weighted ends.  Out of line on
+// purpose: it is the rare path, and inlining its ~160 instructions at every call site bloats the segment loops.
+template <int NM>
+struct AccV {
+    float v[NM];
+};
+
+template <int NM, bool USE_TEX>
+__device__ __noinline__ AccV<NM> w_slow_sample_nl(const VolDev* __restrict__ volp, float x, float y, float z, float weight, AccV<NM> acc) {
+    const VolDev& vol = *volp;
+    float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
+    float bx = floorf(px), by = floorf(py), bz = floorf(pz);
+    int ci = min(max((int)bx + 2, 0), vol.ni), cj = min(max((int)by + 2, 0), vol.nj), ck = min(max((int)bz + 2, 0), vol.nk);
+    uint2 lab8 = __ldg(vol.celll + ((size_t)ck * (vol.nj + 1) + cj) * (vol.ni + 1) + ci);
+    float seg[NM];
+#pragma unroll
+    for (int m = 0; m < NM; m++) seg[m] = 0.0f;
+    seg_weights<NM>(__fsub_rn(px, bx), __fsub_rn(py, by), __fsub_rn(pz, bz), lab8, seg);
+    float cx = __fadd_rn(px, 0.5f), cy = __fadd_rn(py, 0.5f), cz = __fadd_rn(pz, 0.5f);  // K.cu:542
+    float rho = USE_TEX ? tex3D<float>(vol.tex, cx, cy, cz) : hw_trilinear_raw(vol, cx, cy, cz);
+    float wr = __fmul_rn(weight, rho);
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc.v[m] = __fmaf_rn(wr, seg[m], acc.v[m]);
+    return acc;
+}
+
+// out-of-line call (cold paths with many call sites)
+template <int NM, bool USE_TEX>
+__device__ __forceinline__ void w_slow_sample_call(const VolDev& vol, float x, float y, float z, float weight, float* acc) {
+    AccV<NM> a;
+#pragma unroll
+    for (int m = 0; m < NM; m++) a.v[m] = acc[m];
+    a = w_slow_sample_nl<NM, USE_TEX>(&vol, x, y, z, weight, a);
+#pragma unroll
+    for (int m = 0; m < NM; m++) acc[m] = a.v[m];
+}
+
+// inlined (the general-segment loop, where the call overhead shows)
 template <int NM, bool USE_TEX>
 __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float y, float z, float weight, float* acc) {
     float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
@@ -186,7 +223,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                                 if (alpha < los[i] || alpha > his[i] || P.priority[i] != curr_priority) continue;
                                 const float x = __fmaf_rn(alpha, dxs[i], mvw->src[i][0]), y = __fmaf_rn(alpha, dys[i], mvw->src[i][1]),
                                             z = __fmaf_rn(alpha, dzs[i], mvw->src[i][2]);
-                                w_slow_sample<NM, USE_TEX>(P.vol[i], x, y, z, weight, acc);
+                                w_slow_sample_call<NM, USE_TEX>(P.vol[i], x, y, z, weight, acc);
                             }
                         }
                     }
@@ -233,7 +270,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                 const bool inr = (t < num_steps) && !(alpha < lo) && !(alpha > hi);
                 if (inr) {
                     const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
-                    w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);
+                    w_slow_sample_call<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);
                 }
                 alpha = __fadd_rn(alpha, step);
             }
