@@ -206,9 +206,10 @@ def place_kwire(wire: Volume, tip_world, direction_world) -> None:
     wire.world_from_anatomical = geo.FrameTransform.from_rt(r, tip_world)
 
 
-def c3_scene(ct_shape=(512, 512, 400), ct_spacing=(0.8, 0.8, 1.0)) -> List[Volume]:
-    """CT + two K-wires crossing at 20 degrees near the CT centre."""
-    ct = thorax_volume(ct_shape, ct_spacing)
+def c3_scene(ct_shape=(512, 512, 400), ct_spacing=(0.8, 0.8, 1.0), ct: Optional[Volume] = None) -> List[Volume]:
+    """CT + two K-wires crossing at 20 degrees near the CT centre; ``ct`` reuses an existing CT."""
+    if ct is None:
+        ct = thorax_volume(ct_shape, ct_spacing)
     w1, w2 = kwire_volume(), kwire_volume()
     half = math.radians(10.0)
     d1 = np.array([math.sin(half), math.cos(half), 0.2])
