@@ -171,6 +171,43 @@ def test_live_reference_kernel_ct_plus_two_tool_volumes(priorities, enabled):
     ref.close()
 
 
+def test_live_reference_kernel_label_cache_coincidences():
+    """SURVEY.md App. A Q3 at full strength: two volumes on the same voxel grid, offset by less than a voxel, so that the
+    second volume's floored sample coordinates equal the first one's at most steps and the reference serves it the FIRST
+    volume's labels.  The lock-step kernel must detect this per ray and hand those tiles to the step-by-step replay."""
+    from oracle import ref_gpu
+
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not shipped")
+    a = phantoms.thorax_volume((64, 64, 50), (6.4, 6.4, 8.0), seed=7)
+    b = phantoms.thorax_volume((64, 64, 50), (6.4, 6.4, 8.0), seed=8)
+    b.translate((1.9, 1.2, 2.6))                      # 0.3 voxel in every axis
+    volumes, priorities = [a, b], [1, 0]              # b outranks a wherever both are hit
+    st = cases.tables(volumes, "60KV_AL35", priorities)
+    carm = phantoms.MobileCArmGeometry(sensor_width=96, sensor_height=80, pixel_size=3.0)
+    poses = phantoms.c2_poses(2, seed=11, carm=carm)
+    ref = ref_gpu.RefProjector([v.data for v in volumes], st.labels, st.M, lineint=True)
+    with Projector(volumes, priorities=priorities, spectrum="60KV_AL35", neglog=False, camera_intrinsics=carm.camera_intrinsics,
+                   sampler="hybrid") as p:
+        area = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+        p.set_kernel_variant(1)                        # the general kernel alone
+        area_general = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+    # the scene is sensitive to the quirk: listing the same two volumes in the other order (b first: it then always
+    # fetches its own labels) changes the picture
+    with Projector([b, a], priorities=[0, 1], spectrum="60KV_AL35", neglog=False, camera_intrinsics=carm.camera_intrinsics) as p:
+        swapped = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+    assert cases.rel_err(swapped, area)[area > 1.0].max() > 1e-3
+    # a projector that ignored the quirk (own labels always) would be far off: b's bone sampled with a's labels etc.
+    for n, pose in enumerate(poses):
+        w2i, src, ijk = geo.pose_arrays(pose, volumes)
+        li = ref.line_integrals(96, 80, 0.1, w2i, src, ijk, carm.max_ray_length, priority=priorities)
+        for m in range(st.M):
+            mask = li[m] > 0
+            assert cases.rel_err(area[n, m], li[m])[mask].max() <= LINE_RTOL, (n, m)
+            assert cases.rel_err(area_general[n, m], li[m])[mask].max() <= LINE_RTOL, (n, m)
+    ref.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # properties and edge cases
 # ---------------------------------------------------------------------------------------------
