@@ -124,13 +124,16 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_capture():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_bench_ncu.json")))
+    except Exception:
+        return {}
+
+
 def _ncu_traffic():
     """DRAM bytes per launch of the march kernel from the committed ncu capture of this command, if any."""
-    try:
-        j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_ncu.json")))
-        return j.get("march_dram_bytes_per_launch")
-    except Exception:
-        return None
+    return _ncu_capture().get("march_dram_bytes_per_launch")
 
 
 def cpu_baseline_port(volume, st, carm, pose, crop=256):
@@ -259,6 +262,11 @@ def run_ours(args):
                         "binding-resource figures are in 'binding'"}
     binding = {"ray_steps_per_s": samples_per_s, "march_ms_per_view": float(np.mean(march_ms)) / B,
                "steps_per_view": samples / (B * args.steps), "gather_GBps_at_40B_per_step": samples_per_s * 40 / 1e9}
+    cap = _ncu_capture()
+    if cap:  # what actually binds, from the committed ncu capture of this command (profiles/r01_bench_ncu.json)
+        binding["ncu_capture"] = {k: cap.get(k) for k in ("issue_slot_utilisation", "tex_request_cycles_pct", "pipe_fma_pct", "pipe_alu_pct",
+                                                          "shared_pipe_wavefronts_pct", "avg_active_lanes", "l1tex_hit_pct", "l2_hit_pct",
+                                                          "warps_active_pct", "registers_per_thread")}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

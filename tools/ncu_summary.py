@@ -47,7 +47,7 @@ hdr, vals = rows[0], rows[-1]
 m = {hh: vals[k] for k, hh in enumerate(hdr)}
 want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum",
-        "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct",
+        "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tex.avg.pct_of_peak_sustained_active", "l1tex__texin_sm2tex_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -86,7 +86,8 @@ if a.json:
           "march_dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_bytes_read": rd, "dram_bytes_write": wr,
           "algorithmic_bytes_per_launch": a.algorithmic_bytes_per_view * a.views, "duration_ms_under_ncu": in_ms("gpu__time_duration.sum"),
           "warp_instructions": inst, "sm_cycles": cyc,
-          "issue_slot_utilisation": f("smsp__issue_active.avg.pct", 0.01),
+          "issue_slot_utilisation": f("sm__issue_active.avg.pct_of_peak_sustained_elapsed", 0.01),
+          "shared_pipe_wavefronts_pct": f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
           "avg_active_lanes": f("smsp__thread_inst_executed_per_inst_executed.ratio"),
           "l1tex_hit_pct": f("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": f("lts__t_sector_hit_rate.pct"),
           "tex_request_cycles_pct": f("l1tex__texin_sm2tex_req_cycles_active.avg.pct_of_peak_sustained_elapsed"),
@@ -95,6 +96,6 @@ if a.json:
           "pipe_xu_pct": f("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
           "registers_per_thread": f("launch__registers_per_thread"), "grid": f("launch__grid_size"), "block": f("launch__block_size"),
           "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
-          "dram_throughput_pct": f("dram__throughput.avg.pct_of_peak_sustained_elapsed")}
+          "dram_throughput_pct": f("FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed") or f("dram__throughput.avg.pct_of_peak_sustained_elapsed")}
     json.dump(js, open(a.json, "w"), indent=1)
     print("wrote", a.json)
