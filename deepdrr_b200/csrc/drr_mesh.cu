@@ -58,8 +58,9 @@ __global__ void mesh_box_init_kernel(int* __restrict__ prim_box, int n) {
 __global__ void mesh_project_kernel(const ViewDev* __restrict__ views, const float* __restrict__ source_world,
                                     const float* __restrict__ verts_world, const int* __restrict__ prim_of_tri, int n_tris, int n_prims,
                                     int4* __restrict__ tri_box, int* __restrict__ prim_box) {
-    const int tri = blockIdx.x * blockDim.x + threadIdx.x, view = blockIdx.y;
-    if (tri >= n_tris) return;
+    const int tri0 = blockIdx.x * blockDim.x + threadIdx.x, view = blockIdx.y;
+    const bool live = tri0 < n_tris;
+    const int tri = live ? tri0 : n_tris - 1;  // keep the warp whole for the reduction below
     const float* W = views[view].w2i_inv;
     const float* v = verts_world + ((size_t)view * n_tris + tri) * 9;
     const float ox = source_world[3 * view], oy = source_world[3 * view + 1], oz = source_world[3 * view + 2];
@@ -76,9 +77,17 @@ __global__ void mesh_project_kernel(const ViewDev* __restrict__ views, const flo
     int4 b;
     if (unbounded) b = make_int4(-BOX_INF, BOX_INF, -BOX_INF, BOX_INF);
     else b = make_int4((int)floorf(umin - 1.5f), (int)ceilf(umax + 0.5f), (int)floorf(vmin - 1.5f), (int)ceilf(vmax + 0.5f));
-    tri_box[(size_t)view * n_tris + tri] = b;
-    int* pb = prim_box + ((size_t)view * n_prims + prim_of_tri[tri]) * 4;
-    atomicMin(pb + 0, b.x); atomicMax(pb + 1, b.y); atomicMin(pb + 2, b.z); atomicMax(pb + 3, b.w);
+    if (live) tri_box[(size_t)view * n_tris + tri] = b;
+    // union over the primitive: one set of atomics per warp when the warp's triangles belong to one primitive
+    const int prim = prim_of_tri[tri];
+    int* pb = prim_box + ((size_t)view * n_prims + prim) * 4;
+    if (__all_sync(0xffffffffu, prim == __shfl_sync(0xffffffffu, prim, 0))) {
+        const int x0 = __reduce_min_sync(0xffffffffu, b.x), x1 = __reduce_max_sync(0xffffffffu, b.y);
+        const int y0 = __reduce_min_sync(0xffffffffu, b.z), y1 = __reduce_max_sync(0xffffffffu, b.w);
+        if ((threadIdx.x & 31) == 0) { atomicMin(pb + 0, x0); atomicMax(pb + 1, x1); atomicMin(pb + 2, y0); atomicMax(pb + 3, y1); }
+    } else {
+        atomicMin(pb + 0, b.x); atomicMax(pb + 1, b.y); atomicMin(pb + 2, b.z); atomicMax(pb + 3, b.w);
+    }
 }
 
 // Stage those triangles of [base, base + cnt) whose box meets the tile [u0, u1] x [v0, v1], in index order (so sums
