@@ -269,7 +269,7 @@ def run_ours(args):
                                                           "warps_active_pct", "registers_per_thread")}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is reported at N = 1 only
         st = SceneTables([volume], SPECTRUM)
         cpu = cpu_baseline_port(volume, st, carm, poses[0])
     p.free()
