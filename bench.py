@@ -263,6 +263,14 @@ def run_ours(args):
     binding = {"ray_steps_per_s": samples_per_s, "march_ms_per_view": float(np.mean(march_ms)) / B,
                "steps_per_view": samples / (B * args.steps), "gather_GBps_at_40B_per_step": samples_per_s * 40 / 1e9}
     cap = _ncu_capture()
+    if cap.get("tex_lane_fetches_per_launch"):
+        # texture-unit load: fetches per view counted by ncu (SASS TEX instructions x active lanes) x views/s, against the unit's
+        # measured peak of 1.98 trilinear fp32 fetches / clk / SM (tools/tex_rate.cu on a B200: 5.5e11 /s)
+        per_view = cap["tex_lane_fetches_per_launch"] / cap.get("views_per_launch", B)
+        rate = per_view * B / avg_march_s
+        binding["tex_fetches_per_s"] = rate
+        binding["tex_peak_fetches_per_s"] = 5.5e11
+        binding["tex_frac_of_peak"] = rate / 5.5e11
     if cap:  # what actually binds, from the committed ncu capture of this command (profiles/r01_bench_ncu.json)
         binding["ncu_capture"] = {k: cap.get(k) for k in ("issue_slot_utilisation", "tex_request_cycles_pct", "pipe_fma_pct", "pipe_alu_pct",
                                                           "shared_pipe_wavefronts_pct", "avg_active_lanes", "l1tex_hit_pct", "l2_hit_pct",

@@ -23,6 +23,8 @@ h = rows[1]
 ie, src, at, ss = h.index("Instructions Executed"), h.index("Source"), h.index("Avg. Threads Executed"), h.index("# Samples")
 data = [(int(r[ie]), float(r[at]) if r[at] else 0, r[src].strip(), int(r[ss])) for r in rows[2:] if len(r) > ie]
 tot, tots = sum(d[0] for d in data), sum(d[3] for d in data)
+tex_lane_fetches = sum(d[0] * d[1] for d in data if (d[2].split()[1] if d[2].startswith("@") else d[2].split()[0]).startswith("TEX"))
+print("texture fetches (lanes) %.4e" % tex_lane_fetches)
 print("total warp-inst %.3e" % tot, "n sass", len(data), "samples", tots)
 i = 0
 while i < len(data):
@@ -85,7 +87,7 @@ if a.json:
     js = {"command": a.command, "kernel": m.get("Kernel Name", ""), "views_per_launch": a.views,
           "march_dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_bytes_read": rd, "dram_bytes_write": wr,
           "algorithmic_bytes_per_launch": a.algorithmic_bytes_per_view * a.views, "duration_ms_under_ncu": in_ms("gpu__time_duration.sum"),
-          "warp_instructions": inst, "sm_cycles": cyc,
+          "warp_instructions": inst, "sm_cycles": cyc, "tex_lane_fetches_per_launch": tex_lane_fetches,
           "issue_slot_utilisation": f("sm__issue_active.avg.pct_of_peak_sustained_elapsed", 0.01),
           "shared_pipe_wavefronts_pct": f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
           "avg_active_lanes": f("smsp__thread_inst_executed_per_inst_executed.ratio"),
