@@ -151,8 +151,10 @@ __global__ void build_cells_kernel(const float* __restrict__ dens, const uint8_t
         float t01 = T[c][0][1], t10 = T[c][1][0], t00 = T[c][0][0], t11 = T[c][1][1];
         cs[c] = make_float4(t01 * s, (t10 - t01) * s, (t00 - t01) * s, (t11 - t10) * s);
     }
-    cellc[2 * cell] = make_float4(cs[0].x, cs[1].x, cs[0].y, cs[1].y);
-    cellc[2 * cell + 1] = make_float4(cs[0].z, cs[1].z, cs[0].w, cs[1].w);
+    if (cellc != nullptr) {  // absent when the records did not fit in device memory (texture-unit sampler only)
+        cellc[2 * cell] = make_float4(cs[0].x, cs[1].x, cs[0].y, cs[1].y);
+        cellc[2 * cell + 1] = make_float4(cs[0].z, cs[1].z, cs[0].w, cs[1].w);
+    }
     celll[cell] = make_uint2(lx, ly);
     const unsigned l0 = lx & 0xFF;
     const bool uniform = (lx == ly) && (lx == l0 * 0x01010101u);
@@ -424,9 +426,22 @@ static int add_volume_impl(drr_ctx* c, const float* density, const uint8_t* labe
     CUV(cudaGetLastError());
     if (!(flags & 1u)) {
         const size_t ncell = (size_t)(ni + 1) * (nj + 1) * (nk + 1);
-        CUV(cudaMalloc(&v.cellc, ncell * 2 * sizeof(float4)));
         CUV(cudaMalloc(&v.celll, ncell * sizeof(uint2)));
         CUV(cudaMalloc(&v.cellcode, ncell));
+        // The 32 B / cell coefficient records only serve the FMA-pipe sampler.  If they do not fit next to a texture, go
+        // without them: such a volume is sampled by the texture unit alone (drr_project picks the sampler per scene).
+        {
+            size_t free_b = 0, total_b = 0;
+            const size_t want = ncell * 2 * sizeof(float4), tex_bytes = (flags & 2u) ? 0 : n * sizeof(float);
+            cudaError_t e_ = cudaMemGetInfo(&free_b, &total_b);
+            if ((flags & 4u) || (e_ == cudaSuccess && !(flags & 2u) && want + tex_bytes + (size_t)(1u << 28) > free_b)) {
+                v.cellc = nullptr;
+            } else {
+                e_ = cudaMalloc(&v.cellc, want);
+                if (e_ == cudaErrorMemoryAllocation && !(flags & 2u)) { cudaGetLastError(); v.cellc = nullptr; }
+                else CUV(e_);
+            }
+        }
         dim3 cg((ni + 1 + 127) / 128, nj + 1, nk + 1);
         build_cells_kernel<<<cg, 128, 0, s>>>(v.dens, v.lab, ni, nj, nk, v.cellc, v.celll, v.cellcode);
         c->launches += 1;
@@ -926,6 +941,10 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         // Tiles whose rays see a single volume take the lock-step kernel; the others are listed for the general one.
         bool split = !c->attenuate_outside && c->variant == 0;  // (V == 1 gets here only with meshes)
         int sampler = c->sampler;
+        for (int v = 0; v < V; v++)  // a volume without coefficient records: texture unit only; without a texture: FMA pipes only
+            if (!c->vols[v].cellc && c->vols[v].tex) sampler = DRR_SAMPLER_TEX;
+        for (int v = 0; v < V; v++)
+            if (!c->vols[v].tex && sampler != DRR_SAMPLER_TEX) sampler = DRR_SAMPLER_ALU;
         for (int v = 0; v < V && split; v++) {
             const VolHost& h = c->vols[v];
             if (!h.cellcode || (sampler != DRR_SAMPLER_TEX && !h.cellc) || (sampler != DRR_SAMPLER_ALU && !h.tex)) split = false;

@@ -69,11 +69,14 @@ class Projector(object):
         cuda_device_id=None,
         sampler: str = "hybrid",
         noise_seed: Optional[int] = None,
+        coefficient_records: bool = True,
     ) -> None:
         """See the reference docstring (projector.py:423-454).  Extra, optional arguments:
 
         sampler: "hybrid" (default), "alu" or "tex" -- which units fetch the density (same arithmetic).
         noise_seed: seed of the Philox stream used by ``add_noise`` (the reference uses unseeded NumPy).
+        coefficient_records: False skips the 32 B / voxel filter-coefficient records of the FMA-pipe sampler (the library
+            does so by itself when they do not fit in device memory); the texture unit then fetches every sample.
         """
         self.cuda_device_id = cuda_device_id
         self.mesh_layers = mesh_layers
@@ -161,6 +164,7 @@ class Projector(object):
             raise ValueError(f"unknown sampler {sampler!r}")
         self.sampler = sampler
         self.noise_seed = noise_seed
+        self.coefficient_records = bool(coefficient_records)
         self._noise_calls = 0
 
         self.output_shape = None
@@ -218,18 +222,19 @@ class Projector(object):
             self._energies, self._pdf, self._mu = energies, pdf, mu
             _lib.check(lib.drr_set_spectrum(h, len(energies), len(self.all_materials), _lib.ptr(energies), _lib.ptr(pdf),
                                             _lib.ptr(mu)), h)
+            vol_flags = 0 if self.coefficient_records else 4
             for _vol in self.volumes:
                 if isinstance(_vol, vol.HUVolume):  # HU -> density + segmentation on the device
                     cls = np.array([self.all_materials.index(k) for k in ("air", "soft tissue", "bone")], dtype=np.int32)
                     vid = ctypes.c_int(-1)
                     _lib.check(lib.drr_add_volume_hu(h, _lib.ptr(_vol.hu), _vol.hu.shape[0], _vol.hu.shape[1], _vol.hu.shape[2], _lib.MEM_HOST,
-                                                     _lib.ptr(cls), 0, ctypes.byref(vid)), h)
+                                                     _lib.ptr(cls), vol_flags, ctypes.byref(vid)), h)
                     continue
                 dens = np.ascontiguousarray(np.asarray(_vol.data), dtype=np.float32)
                 labels = np.ascontiguousarray(remap_labels(_vol, self.all_materials))
                 vid = ctypes.c_int(-1)
                 _lib.check(lib.drr_add_volume(h, _lib.ptr(dens), _lib.ptr(labels), dens.shape[0], dens.shape[1], dens.shape[2],
-                                              _lib.MEM_HOST, 0, ctypes.byref(vid)), h)
+                                              _lib.MEM_HOST, vol_flags, ctypes.byref(vid)), h)
             self._mesh_state = None
             self._upload_meshes()
             if self.scatter_num > 0:

@@ -71,7 +71,9 @@ int drr_set_spectrum(drr_ctx* ctx, int n_bins, int n_materials, const float* ene
  * (projector.py:1463-1546, 116-257).  Builds on the device, from one upload of the raw arrays:
  * the [k][j][i] density/label arrays, the 3-D CUDA array + texture object, and the per-cell records
  * the ALU sampler marches over.  Returns the volume index in *vol_id (order = kernel volume order).
- * flags: bit0 = skip cell records (TEX-only handle), bit1 = skip texture (ALU-only handle). */
+ * flags: bit0 = skip cell records (TEX-only handle), bit1 = skip texture (ALU-only handle), bit2 = skip only the
+ * 32 B / cell filter-coefficient records (done automatically when they do not fit in device memory: the volume is then
+ * sampled by the texture unit alone). */
 int drr_add_volume(drr_ctx* ctx, const float* density, const uint8_t* labels, int ni, int nj, int nk, int mem_kind,
                    unsigned flags, int* vol_id);
 /* Same, from a Hounsfield-unit volume: HU -> density (vol/volume.py:338-351) and threshold segmentation

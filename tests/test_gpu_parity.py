@@ -69,6 +69,26 @@ def test_full_size_c2_vs_reference_kernel_golden():
     _compare_with_golden("c2", ("hybrid", "alu"), views=[0])
 
 
+def test_without_coefficient_records_everything_runs_on_the_texture_unit():
+    """What the library does by itself when the 32 B / voxel records of the FMA-pipe sampler do not fit in device memory:
+    the scene is sampled by the texture unit alone, single- and multi-volume, and still matches the reference goldens."""
+    for name in ("thorax_small", "multivol3"):
+        volumes, spectrum, priorities = cases.scene(name)
+        g = cases.golden(name)
+        W, H, sub = int(g["W"]), int(g["H"]), int(g["sub"])
+        with Projector(volumes, priorities=priorities, spectrum=spectrum, step=float(g["step"]), neglog=False,
+                       camera_intrinsics=geo.CameraIntrinsicTransform.from_sizes((W, H), 1.0, 1000.0), sampler="hybrid",
+                       coefficient_records=False) as p:
+            area = p.project_arrays(g["w2i_0"].reshape(1, 9), g["src_0"].reshape(1, -1, 3), g["ijk_0"].reshape(1, -1, 12), (W, H),
+                                    float(g["max_ray_length"]), want="area")[0]
+        gl = g["lineint_0"]
+        a = area[:, ::sub, ::sub]
+        for m in range(a.shape[0]):
+            mask = gl[m] > 0
+            if mask.any():
+                assert cases.rel_err(a[m], gl[m])[mask].max() <= LINE_RTOL, (name, m)
+
+
 def test_per_ray_kernel_variant_matches_too():
     volumes, spectrum, priorities = cases.scene("c1")
     g = cases.golden("c1")
