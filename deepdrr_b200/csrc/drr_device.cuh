@@ -109,6 +109,33 @@ __device__ __forceinline__ bool slab_test(float dx, float dy, float dz, float sx
 }
 
 // ---------------------------------------------------------------------------------------------
+// alpha after n sequential fp32 additions of step -- exactly what n times "alpha += step" (K.cu:552) gives, without
+// doing them one by one.  Inside one binade every partial sum lands on the same ulp grid, so each addition moves alpha
+// by the same whole number of ulps D (step rounded to that grid; the exact sum stays below the top of the binade, so the
+// grid cannot change under it): m additions are one integer multiply-add on the bit pattern.  Additions that leave the
+// binade, and binades where step falls exactly between two grid points (round-to-even then depends on the parity of
+// alpha), are taken one at a time.  alpha > 0 normal, step > 0.  Checked against the plain loop on 460 000 random
+// (alpha, step, n) on the host, ties and powers of two included.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float alpha_jump(float alpha, float step, int n) {
+    while (n > 0) {
+        const float next = __fadd_rn(alpha, step);
+        const unsigned ua = __float_as_uint(alpha), un = __float_as_uint(next);
+        if ((ua >> 23) != (un >> 23) || n == 1) { alpha = next; n--; continue; }
+        const unsigned D = un - ua;
+        if (D == 0u) return alpha;  // step is below half an ulp: alpha no longer moves
+        const float r = __fsub_rn(step, __fsub_rn(next, alpha));             // both subtractions are exact
+        const float ulp = __uint_as_float(((ua >> 23) - 23u) << 23);
+        unsigned m = (0x7FFFFFu - (ua & 0x7FFFFFu)) / D;                      // additions that stay inside the binade
+        if (__fmul_rn(fabsf(r), 2.0f) == ulp || m == 0u) { alpha = next; n--; continue; }
+        m = min(m, (unsigned)n);
+        alpha = __uint_as_float(ua + m * D);
+        n -= (int)m;
+    }
+    return alpha;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Texture-unit arithmetic, integer form (general / boundary path)
 // ---------------------------------------------------------------------------------------------
 // Q = clamp(floor((c - 0.5) * 256 + 0.5), 0, (n - 1) * 256) for texture coordinate c.

@@ -156,7 +156,11 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             }
         }
         const int n_skip = __reduce_min_sync(0xffffffffu, n0);
-        for (; t < n_skip; t++) alpha = __fadd_rn(alpha, step);
+        if (num_steps > 0) {  // (lanes without a ray have nothing to keep in step)
+            if (alpha >= 0x1p-100f) alpha = alpha_jump(alpha, step, n_skip);  // == n_skip times alpha += step
+            else for (int i = 0; i < n_skip; i++) alpha = __fadd_rn(alpha, step);
+        }
+        t = n_skip;
     }
 
     float cur = 0.0f;
