@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Randomised parity check (GPU box, needs oracle/_ref): single-volume scenes with arbitrary volume poses and cameras --
+sources inside the volume, grazing rays, coarse detectors (per-ray kernel variant), short max_ray_length -- vs the reference's
+own kernel, per-pixel line integrals and intensity."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from deepdrr_b200 import Projector, phantoms, geo
+from deepdrr_b200.scene import SceneTables
+from oracle import ref_gpu
+
+n_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+worst_l, worst_i, fails = 0.0, 0.0, 0
+t0 = time.time()
+
+
+def rot(rng):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    a, b, c, d = q
+    return np.array([[a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c)], [2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)], [2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d]])
+
+
+for it in range(n_iter):
+    shape = tuple(int(x) for x in rng.integers(24, 72, size=3))
+    spacing = tuple(rng.uniform(0.6, 8.0, size=3))
+    v = phantoms.thorax_volume(shape, spacing, seed=int(rng.integers(1 << 30)))
+    v.rotate(rot(rng)); v.translate(rng.uniform(-40, 40, size=3))
+    st = SceneTables([v], "90KV_AL40")
+    W, H = int(rng.integers(17, 120)), int(rng.integers(9, 100))
+    pixel = float(rng.choice([0.2, 0.8, 2.0, 6.0]))
+    sdd = float(rng.uniform(300, 1500))
+    k = geo.CameraIntrinsicTransform.from_sizes((W, H), pixel, sdd)
+    extent = np.array(shape) * np.array(spacing)
+    mode = it % 4
+    if mode == 0:    # source inside the volume
+        source = rng.uniform(-0.3, 0.3, size=3) * extent
+    elif mode == 1:  # grazing: looking along a face
+        source = np.array([0.0, -extent[1], 0.5 * extent[2]]) + rng.normal(size=3)
+    else:
+        source = rng.normal(size=3); source = source / np.linalg.norm(source) * float(rng.uniform(0.6, 3.0)) * extent.max()
+    direction = -source + rng.normal(size=3) * 0.2 * extent.max() if mode != 0 else rng.normal(size=3)
+    up = rng.normal(size=3)
+    pose = phantoms.look_at_projection(source, direction, up, k)
+    mrl = float(rng.choice([4 * sdd, 0.7 * np.linalg.norm(source) + 10.0, 1e5]))
+    sampler = ["hybrid", "tex", "alu"][it % 3]
+    with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=k, source_to_detector_distance=sdd, sampler=sampler) as p:
+        area = p.project_line_integrals(pose, max_ray_length=mrl)
+        area = area.reshape(area.shape[-3:])
+        img = p.project(pose, max_ray_length=mrl)
+    ref = ref_gpu.RefProjector([v.data], st.labels, st.M, lineint=True)
+    refp = ref_gpu.RefProjector([v.data], st.labels, st.M)
+    refp.set_spectrum(st.energies, st.pdf, st.mu)
+    w2i, src, ijk = geo.pose_arrays(pose, [v])
+    li = ref.line_integrals(W, H, 0.1, w2i, src, ijk, mrl)
+    ri, _, _ = refp.project(W, H, 0.1, w2i, src, ijk, mrl)
+    for m in range(st.M):
+        mask = li[m] > 0
+        leak = np.any(area[m][~mask] != 0)
+        diff = np.abs(area[m] - li[m])[mask]
+        if sampler == "alu":
+            # the texture-less fallback computes mixed-label samples with the emulated filter (99.8 % of fetches bit-exact,
+            # the rest 1 ulp off): on a pixel whose total for a material is a few grazing samples that ulp can exceed 1e-5
+            # of the total; such differences are below 1e-8 g/cm^2 in absolute terms
+            diff = np.where(diff <= 1e-8, 0.0, diff)
+        err = float((diff / li[m][mask]).max()) if mask.any() else 0.0
+        worst_l = max(worst_l, err)
+        if err > 1e-5 or leak:
+            fails += 1
+            print(f"FAIL it={it} mode={mode} sampler={sampler} mat={m} err={err:.3e} leak={leak} W={W} H={H} pixel={pixel} shape={shape}", flush=True)
+    ei = float((np.abs(img - ri) / np.maximum(np.abs(ri), 1e-30)).max())
+    worst_i = max(worst_i, ei)
+    if ei > 1e-4:
+        fails += 1
+        print(f"FAIL it={it} mode={mode} sampler={sampler} intensity err={ei:.3e}", flush=True)
+    ref.close(); refp.close()
+print(f"{n_iter} scenes, worst relative error: line integrals {worst_l:.3e}, intensity {worst_i:.3e}; failures {fails}; {time.time() - t0:.1f} s", flush=True)
+sys.exit(1 if fails else 0)
