@@ -193,7 +193,7 @@ struct drr_ctx {
     // march options
     float step = 0.1f;
     int attenuate_outside = 0, air_index = 0, sampler = DRR_SAMPLER_HYBRID;
-    int tex_eighths = 5;
+    int tex_eighths = 4;
     int variant = 0;  // 0: warp-cooperative march (default), 1: per-ray register-cell march
     // mesh buffers (device pointers, possibly owned)
     int mesh_layers = 0, max_hits = 0, n_mesh_mats = 0;

@@ -254,6 +254,31 @@ __device__ __forceinline__ float hw_trilinear_cell2(float xr, float yr, float zr
     return __fadd_rn(r.x, r.y);
 }
 
+// The same filter from the texture unit's own fixed-point coordinates.  q* = 0x4B000000 + Q with Q = RHU(256 * l) the 1.8
+// fixed-point coordinate relative to the staged box (one FFMA.RM per axis, see march_core): the low byte is the
+// fraction a in [0, 255], the next byte the cell.  A fraction that rounds up to 256 has already moved Q into the next
+// cell with a = 0 -- exactly what the unit does -- so the x = 0 rule needs no special case here.
+__device__ __forceinline__ float hw_trilinear_cell2q(unsigned qx, unsigned qy, unsigned qz, const float4& A, const float4& B) {
+    const float C = DRR_MAGIC;
+    const float af = __fsub_rn(__uint_as_float(qx & 0xFF8000FFu), 8388608.0f);   // exact: 2^23 + a - 2^23
+    const float bf = __fsub_rn(__uint_as_float(qy & 0xFF8000FFu), 8388608.0f);
+    const float cf = __fsub_rn(__uint_as_float(qz & 0xFF8000FFu), 8388608.0f);
+    const float bp = __fmaf_rn(bf, 0x1p-8f, 0x1p-17f);
+    const float bq = __fmaf_rn(bf, -0x1p-8f, 1.0f + 0x1p-17f);
+    const float2 cc = make_float2(cf, cf), CC = make_float2(C, C), nCC = make_float2(-C, -C);
+    const float2 wz = __ffma2_rn(cc, make_float2(-1.0f, 1.0f), make_float2(256.0f, 0.0f));                        // (256 - c, c)
+    const float2 wp = __ffma2_rn(cc, make_float2(-0x1p-8f, 0x1p-8f), make_float2(1.0f + 0x1p-17f, 0x1p-17f));      // wz/256 + 2^-17
+    const float2 X1 = __fadd2_rn(__ffma2_rn(wp, make_float2(af, af), CC), nCC);
+    const float2 X0 = __ffma2_rn(X1, make_float2(-1.0f, -1.0f), wz);
+    const float2 Y11 = __fadd2_rn(__ffma2_rn(X1, make_float2(bp, bp), CC), nCC);
+    const float2 Y00 = __fadd2_rn(__ffma2_rn(X0, make_float2(bq, bq), CC), nCC);
+    float2 r = __fmul2_rn(wz, make_float2(A.x, A.y));
+    r = __ffma2_rn(X1, make_float2(A.z, A.w), r);
+    r = __ffma2_rn(Y00, make_float2(B.x, B.y), r);
+    r = __ffma2_rn(Y11, make_float2(B.z, B.w), r);
+    return __fadd_rn(r.x, r.y);
+}
+
 // Trilinear one-hot material weights of the reference (K.cu:434-455), full fp32 weights.
 // lab8: byte (dx + 2*dy + 4*dz) = label of corner (dx, dy, dz).  seg[] must be zeroed by the caller.
 template <int NM>

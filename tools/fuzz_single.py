@@ -22,12 +22,16 @@ def rot(rng):
     return np.array([[a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c)], [2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)], [2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d]])
 
 
+only = int(sys.argv[3]) if len(sys.argv) > 3 else None   # replay one iteration (same random stream) and print details
 for it in range(n_iter):
     shape = tuple(int(x) for x in rng.integers(24, 72, size=3))
     spacing = tuple(rng.uniform(0.6, 8.0, size=3))
-    v = phantoms.thorax_volume(shape, spacing, seed=int(rng.integers(1 << 30)))
-    v.rotate(rot(rng)); v.translate(rng.uniform(-40, 40, size=3))
-    st = SceneTables([v], "90KV_AL40")
+    vseed = int(rng.integers(1 << 30))
+    vrot, vtr = rot(rng), rng.uniform(-40, 40, size=3)
+    if only is None or it == only:
+        v = phantoms.thorax_volume(shape, spacing, seed=vseed)
+        v.rotate(vrot); v.translate(vtr)
+        st = SceneTables([v], "90KV_AL40")
     W, H = int(rng.integers(17, 120)), int(rng.integers(9, 100))
     pixel = float(rng.choice([0.2, 0.8, 2.0, 6.0]))
     sdd = float(rng.uniform(300, 1500))
@@ -45,6 +49,29 @@ for it in range(n_iter):
     pose = phantoms.look_at_projection(source, direction, up, k)
     mrl = float(rng.choice([4 * sdd, 0.7 * np.linalg.norm(source) + 10.0, 1e5]))
     sampler = ["hybrid", "tex", "alu"][it % 3]
+    if only is not None and it != only:
+        continue
+    if only is not None:
+        w2i, src, ijk = geo.pose_arrays(pose, [v])
+        ref = ref_gpu.RefProjector([v.data], st.labels, st.M, lineint=True)
+        li = ref.line_integrals(W, H, 0.1, w2i, src, ijk, mrl)
+        for share in (0, 4, 5, 6, 7, 8):
+            with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=k, source_to_detector_distance=sdd, sampler="hybrid") as p:
+                p.set_hybrid_share(share)
+                a = p.project_line_integrals(pose, max_ray_length=mrl); a = a.reshape(a.shape[-3:])
+            rel = np.abs(a[0] - li[0]) / np.maximum(li[0], 1e-30) * (li[0] > 0)
+            print(f"share {share}: air rel err at (45,32) {rel[45, 32] if rel.shape[0] > 45 and rel.shape[1] > 32 else -1:.3e}; max {rel.max():.3e}; pixels above 2e-6: {(rel > 2e-6).sum()} of {(li[0] > 0).sum()}", flush=True)
+        for smp in ("alu",):
+            for variant in (0,):
+                with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=k, source_to_detector_distance=sdd, sampler=smp) as p:
+                    p.set_kernel_variant(variant)
+                    a = p.project_line_integrals(pose, max_ray_length=mrl); a = a.reshape(a.shape[-3:])
+                for m in range(st.M):
+                    mask = li[m] > 0
+                    rel = np.where(mask, np.abs(a[m] - li[m]) / np.maximum(li[m], 1e-30), 0)
+                    idx = np.unravel_index(np.argmax(rel), rel.shape)
+                    print(f"sampler {smp} variant {variant} mat {m}: max rel {rel.max():.3e} at {idx}: ours {a[m][idx]:.9e} ref {li[m][idx]:.9e} (other mats there: {[float(li[q][idx]) for q in range(st.M)]})", flush=True)
+        sys.exit(0)
     with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=k, source_to_detector_distance=sdd, sampler=sampler) as p:
         area = p.project_line_integrals(pose, max_ray_length=mrl)
         area = area.reshape(area.shape[-3:])
