@@ -293,9 +293,12 @@ __device__ __forceinline__ void seg_weights(float fx, float fy, float fz, uint2 
             for (int a = 0; a < 2; a++) {
                 float w = __fmul_rn(__fmul_rn(a ? fx : gx, b ? fy : gy), c ? fz : gz);
                 unsigned word = c ? lab8.y : lab8.x;
-                int l = (word >> (8 * (a + 2 * b))) & 0xFF;
+                int l = (int)__byte_perm(word, 0u, 0x4440u + (a + 2 * b));
+                // one predicated add per material (adding 0.0f to the others, as a select would, changes nothing); written
+                // in PTX because the compiler turns the C++ form into select + add or into branches
 #pragma unroll
-                for (int m = 0; m < NM; m++) seg[m] = __fadd_rn(seg[m], (l == m) ? w : 0.0f);
+                for (int m = 0; m < NM; m++)
+                    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.rn.f32 %0, %0, %1;\n\t}" : "+f"(seg[m]) : "f"(w), "r"(l), "r"(m));
             }
         }
     }

@@ -349,7 +349,8 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         const bool seg_allin = __all_sync(0xffffffffu, lane_allin);
 
         const float b1x = (float)(blx + 1), b1y = (float)(bly + 1), b1z = (float)(blz + 1);
-        const float fnx = (float)nx, fny = (float)ny;
+        const unsigned cell_w = 1u | ((unsigned)min(nx, 255) << 8) | ((unsigned)min(nx * ny, 255) << 16);  // idx = cx + nx * cy + nx * ny * cz as one dp4a
+        const float kfx = __fmaf_rn(-256.0f, b1x, 8388608.0f), kfy = __fmaf_rn(-256.0f, b1y, 8388608.0f), kfz = __fmaf_rn(-256.0f, b1z, 8388608.0f);
         if (seg_uniform && seg_allin) {
             // ---- 3a. fast segment: one label, no range checks ------------------------------------
             if (live != code0) {
@@ -365,9 +366,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             // kq = 2^23 + 0.5 - 256 * b1 is exact (b1 >= 2 on interior cells, so kq < 2^23 where the grid is 0.5), the FMA
             // adds it to 256 * x without intermediate rounding, the sum is >= 2^23 (grid 1) and rounding DOWN leaves
             // 2^23 + Q in the mantissa: low byte = fraction, next byte = cell (box sides are < 256 cells).
-            const float kqx = __fadd_rn(__fmaf_rn(-256.0f, b1x, 8388608.0f), 0.5f), kqy = __fadd_rn(__fmaf_rn(-256.0f, b1y, 8388608.0f), 0.5f),
-                        kqz = __fadd_rn(__fmaf_rn(-256.0f, b1z, 8388608.0f), 0.5f);
-            const unsigned cell_w = 1u | ((unsigned)min(nx, 255) << 8) | ((unsigned)min(nx * ny, 255) << 16);  // idx = cx + nx * cy + nx * ny * cz
+            const float kqx = __fadd_rn(kfx, 0.5f), kqy = __fadd_rn(kfy, 0.5f), kqz = __fadd_rn(kfz, 0.5f);
             auto alu_sample = [&](float a) {
                 const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
                 const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kqx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kqy)),
@@ -435,14 +434,17 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                     const float a = aj[j];
                     const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
                     const bool inr = (t < num_steps) && !(a < lo) && !(a > hi);  // K.cu:472
-                    // cell-local coordinates: l = p - box_lo, p = x - 1 (K.cu:402-404); exact for x >= 1
-                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
-                    int idx = (int)__fmaf_rn(__fmaf_rn(fbz, fny, fby), fnx, fbx);
-                    idx = inr ? min(max(idx, 0), ncell - 1) : 0;
+                    // cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1)) from one round-down
+                    // FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte
+                    const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
+                                   qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
+                    int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
+                    idx = inr ? min(idx, ncell - 1) : 0;
                     int code = s_code[idx];
                     if ((t == 0) | (t == last)) code = 0xFF;  // half-weighted end samples take the generic path
-                    if (inr) {
+                    if (USE_TEX && __all_sync(0xffffffffu, !inr || code == live)) {
+                        cur = __fadd_rn(cur, rj[j]);  // the whole warp stays on its material (lanes out of range fetched nothing: + 0)
+                    } else if (inr) {
                         if (code != live) {
                             w_checkin<NM>(cur, live, acc);
                             if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
@@ -451,6 +453,9 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                             if (USE_TEX) {
                                 cur = __fadd_rn(cur, rj[j]);
                             } else if (STAGE_COEF) {
+                                // cell-local coordinates: l = p - box_lo; exact for x >= 1
+                                const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                                const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
                                 const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
                                 cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
                             }
