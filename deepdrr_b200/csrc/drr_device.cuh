@@ -260,13 +260,11 @@ __device__ __forceinline__ float hw_trilinear_cell2(float xr, float yr, float zr
 // cell with a = 0 -- exactly what the unit does -- so the x = 0 rule needs no special case here.
 __device__ __forceinline__ float hw_trilinear_cell2q(unsigned qx, unsigned qy, unsigned qz, const float4& A, const float4& B) {
     const float C = DRR_MAGIC;
-    const float af = __fsub_rn(__uint_as_float(qx & 0xFF8000FFu), 8388608.0f);   // exact: 2^23 + a - 2^23
-    const float bf = __fsub_rn(__uint_as_float(qy & 0xFF8000FFu), 8388608.0f);
-    const float cf = __fsub_rn(__uint_as_float(qz & 0xFF8000FFu), 8388608.0f);
+    const float af = (float)(qx & 0xFFu), bf = (float)(qy & 0xFFu), cf = (float)(qz & 0xFFu);  // I2FP: off the FMA pipes, which bind this loop
     const float bp = __fmaf_rn(bf, 0x1p-8f, 0x1p-17f);
     const float bq = __fmaf_rn(bf, -0x1p-8f, 1.0f + 0x1p-17f);
     const float2 cc = make_float2(cf, cf), CC = make_float2(C, C), nCC = make_float2(-C, -C);
-    const float2 wz = __ffma2_rn(cc, make_float2(-1.0f, 1.0f), make_float2(256.0f, 0.0f));                        // (256 - c, c)
+    const float2 wz = make_float2(__fsub_rn(256.0f, cf), cf);                                                     // (256 - c, c)
     const float2 wp = __ffma2_rn(cc, make_float2(-0x1p-8f, 0x1p-8f), make_float2(1.0f + 0x1p-17f, 0x1p-17f));      // wz/256 + 2^-17
     const float2 X1 = __fadd2_rn(__ffma2_rn(wp, make_float2(af, af), CC), nCC);
     const float2 X0 = __ffma2_rn(X1, make_float2(-1.0f, -1.0f), wz);
