@@ -422,49 +422,67 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             aj[0] = alpha;
 #pragma unroll
             for (int j = 1; j < 4; j++) aj[j] = __fadd_rn(aj[j - 1], step);  // K.cu:552
+            // per step: in range?  (K.cu:472) -- then the texture fetches of the group, all in flight together
+            bool inr[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                inr[j] = j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi);
                 rj[j] = 0.0f;
-                if (USE_TEX && j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi))
+                if (USE_TEX && inr[j])
                     rj[j] = tex3D<float>(vol.tex, __fsub_rn(__fmaf_rn(aj[j], dx, sx), 0.5f), __fsub_rn(__fmaf_rn(aj[j], dy, sy), 0.5f),
                                          __fsub_rn(__fmaf_rn(aj[j], dz, sz), 0.5f));  // K.cu:542
             }
+            // label code of every sample's cell.  Cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1))
+            // from one round-down FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte.
+            unsigned codes = 0;  // one byte per step
+            bool plain = true;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (j < nb) {
-                    const float a = aj[j];
-                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                    const bool inr = (t < num_steps) && !(a < lo) && !(a > hi);  // K.cu:472
-                    // cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1)) from one round-down
-                    // FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte
-                    const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
-                                   qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
-                    int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
-                    idx = inr ? min(idx, ncell - 1) : 0;
-                    int code = s_code[idx];
-                    if ((t == 0) | (t == last)) code = 0xFF;  // half-weighted end samples take the generic path
-                    if (USE_TEX && __all_sync(0xffffffffu, !inr || code == live)) {
-                        cur = __fadd_rn(cur, rj[j]);  // the whole warp stays on its material (lanes out of range fetched nothing: + 0)
-                    } else if (inr) {
-                        if (code != live) {
-                            w_checkin<NM>(cur, live, acc);
-                            if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
-                        }
-                        if (code != 0xFF) {
-                            if (USE_TEX) {
-                                cur = __fadd_rn(cur, rj[j]);
-                            } else if (STAGE_COEF) {
-                                // cell-local coordinates: l = p - box_lo; exact for x >= 1
-                                const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-                                const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
-                                const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
-                                cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                const float a = aj[j];
+                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
+                               qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
+                int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
+                idx = inr[j] ? min(idx, ncell - 1) : 0;
+                int code = s_code[idx];
+                if ((t + j == 0) | (t + j == last)) code = 0xFF;  // half-weighted end samples take the generic path
+                codes |= (unsigned)code << (8 * j);
+                plain = plain && (!inr[j] || code == live);
+            }
+            if (USE_TEX && __all_sync(0xffffffffu, plain)) {
+                // the whole warp stays on its materials for the group (lanes out of range fetched nothing: + 0)
+#pragma unroll
+                for (int j = 0; j < 4; j++) cur = __fadd_rn(cur, rj[j]);
+                t += nb;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < nb) {
+                        const int code = (int)((codes >> (8 * j)) & 0xFFu);
+                        if (inr[j]) {
+                            if (code != live) {
+                                w_checkin<NM>(cur, live, acc);
+                                if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
                             }
-                        } else {
-                            w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                            const float a = aj[j];
+                            const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                            if (code != 0xFF) {
+                                if (USE_TEX) {
+                                    cur = __fadd_rn(cur, rj[j]);
+                                } else if (STAGE_COEF) {
+                                    // cell-local coordinates: l = p - box_lo; exact for x >= 1
+                                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                                    const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, (float)ny, fby), (float)nx, fbx);
+                                    const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
+                                    cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                                }
+                            } else {
+                                w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                            }
                         }
+                        t++;
                     }
-                    t++;
                 }
             }
             float a_last = aj[0];
