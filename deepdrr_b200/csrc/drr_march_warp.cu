@@ -17,6 +17,8 @@
 // Warps of both roles share every SM, so the TEX pipe and the FMA pipes are busy together.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "drr_device.cuh"
 
 #define TILE_W 8
@@ -422,33 +424,39 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             aj[0] = alpha;
 #pragma unroll
             for (int j = 1; j < 4; j++) aj[j] = __fadd_rn(aj[j - 1], step);  // K.cu:552
-            // per step: in range?  (K.cu:472) -- then the texture fetches of the group, all in flight together
-            bool inr[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                inr[j] = j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi);
-                rj[j] = 0.0f;
-                if (USE_TEX && inr[j])
-                    rj[j] = tex3D<float>(vol.tex, __fsub_rn(__fmaf_rn(aj[j], dx, sx), 0.5f), __fsub_rn(__fmaf_rn(aj[j], dy, sy), 0.5f),
-                                         __fsub_rn(__fmaf_rn(aj[j], dz, sz), 0.5f));  // K.cu:542
-            }
-            // label code of every sample's cell.  Cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1))
+            // per step: in range?  (K.cu:472) -- then the texture fetches of the group, all in flight together -- then the label
+            // code of every sample's cell.  Cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1))
             // from one round-down FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte.
+            // Two copies of this front part: segments whose lanes are all inside their windows (most general segments are
+            // "box not uniform" ones) need neither the range tests nor the end-sample test.
+            bool inr[4];
             unsigned codes = 0;  // one byte per step
             bool plain = true;
+            auto front = [&](auto all_inside) {
+                constexpr bool AI = decltype(all_inside)::value;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float a = aj[j];
-                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
-                               qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
-                int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
-                idx = inr[j] ? min(idx, ncell - 1) : 0;
-                int code = s_code[idx];
-                if ((t + j == 0) | (t + j == last)) code = 0xFF;  // half-weighted end samples take the generic path
-                codes |= (unsigned)code << (8 * j);
-                plain = plain && (!inr[j] || code == live);
-            }
+                for (int j = 0; j < 4; j++) {
+                    inr[j] = AI ? true : (j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi));
+                    const float a = aj[j];
+                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                    rj[j] = 0.0f;
+                    if (USE_TEX && inr[j]) rj[j] = tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float a = aj[j];
+                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
+                    const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
+                                   qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
+                    int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
+                    idx = inr[j] ? min(idx, ncell - 1) : 0;
+                    int code = s_code[idx];
+                    if (!AI && ((t + j == 0) | (t + j == last))) code = 0xFF;  // half-weighted end samples take the generic path
+                    codes |= (unsigned)code << (8 * j);
+                    plain = plain && (!inr[j] || code == live);
+                }
+            };
+            if (seg_allin && nb == 4) front(std::true_type{}); else front(std::false_type{});
             if (USE_TEX && __all_sync(0xffffffffu, plain)) {
                 // the whole warp stays on its materials for the group (lanes out of range fetched nothing: + 0)
 #pragma unroll
