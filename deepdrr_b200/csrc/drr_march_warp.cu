@@ -110,8 +110,11 @@ __device__ __forceinline__ void w_slow_sample_call(const VolDev& vol, float x, f
 }
 
 // inlined (the general-segment loop, where the call overhead shows)
+// `fetched` / `have_fetched`: the density already fetched for this sample at (x - 0.5, y - 0.5, z - 0.5) by the group front.
+// For x, y, z >= 1 that is the reference's own coordinate: x - 1 and (x - 1) + 0.5 are both exact there, so it equals x - 0.5.
 template <int NM, bool USE_TEX>
-__device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float y, float z, float weight, float* acc) {
+__device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float y, float z, float weight, float* acc, float fetched = 0.0f,
+                                              bool have_fetched = false) {
     float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
     float bx = floorf(px), by = floorf(py), bz = floorf(pz);
     int ci = min(max((int)bx + 2, 0), vol.ni), cj = min(max((int)by + 2, 0), vol.nj), ck = min(max((int)bz + 2, 0), vol.nk);
@@ -123,7 +126,9 @@ __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float 
     float cx = __fadd_rn(px, 0.5f), cy = __fadd_rn(py, 0.5f), cz = __fadd_rn(pz, 0.5f);  // K.cu:542
     // mixed-label samples go through the texture unit whenever the volume has a texture, also under the FMA-pipe sampler:
     // the emulated filter is 1 ulp off in 0.2 % of fetches, which shows on pixels whose total for a material is tiny
-    float rho = (USE_TEX || vol.tex != 0) ? tex3D<float>(vol.tex, cx, cy, cz) : hw_trilinear_raw(vol, cx, cy, cz);
+    float rho = fetched;
+    if (!(have_fetched && x >= 1.0f && y >= 1.0f && z >= 1.0f))
+        rho = (USE_TEX || vol.tex != 0) ? tex3D<float>(vol.tex, cx, cy, cz) : hw_trilinear_raw(vol, cx, cy, cz);
     float wr = __fmul_rn(weight, rho);
 #pragma unroll
     for (int m = 0; m < NM; m++) acc[m] = __fmaf_rn(wr, seg[m], acc[m]);
@@ -486,7 +491,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                                     cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
                                 }
                             } else {
-                                w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);  // K.cu:537
+                                w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc, rj[j], USE_TEX);  // K.cu:537
                             }
                         }
                         t++;
