@@ -379,6 +379,8 @@ static int add_volume_impl(drr_ctx* c, const float* density, const uint8_t* labe
     if ((!hu && (!density || !labels)) || ni <= 0 || nj <= 0 || nk <= 0) return fail(c, DRR_E_INVALID, "drr_add_volume: bad arguments");
     if ((int)c->vols.size() >= DRR_MAX_VOLUMES) return fail(c, DRR_E_INVALID, "drr_add_volume: at most %d volumes", DRR_MAX_VOLUMES);
     if (ni > 16384 || nj > 16384 || nk > 16384) return fail(c, DRR_E_INVALID, "drr_add_volume: dimension above 16384");
+    if ((size_t)(ni + 1) * (nj + 1) * (nk + 1) >= ((size_t)1 << 31))  // 8.6 GB of density alone; the march kernels index cells with 32 bits
+        return fail(c, DRR_E_INVALID, "drr_add_volume: more than 2^31 voxel cells");
     CU(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const size_t n = (size_t)ni * nj * nk;

@@ -83,7 +83,7 @@ __device__ __noinline__ AccV<NM> w_slow_sample_nl(const VolDev* __restrict__ vol
     float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
     float bx = floorf(px), by = floorf(py), bz = floorf(pz);
     int ci = min(max((int)bx + 2, 0), vol.ni), cj = min(max((int)by + 2, 0), vol.nj), ck = min(max((int)bz + 2, 0), vol.nk);
-    uint2 lab8 = __ldg(vol.celll + ((size_t)ck * (vol.nj + 1) + cj) * (vol.ni + 1) + ci);
+    uint2 lab8 = __ldg(vol.celll + ((unsigned)ck * (unsigned)(vol.nj + 1) + (unsigned)cj) * (unsigned)(vol.ni + 1) + (unsigned)ci);  // < 2^31 cells (drr_add_volume)
     float seg[NM];
 #pragma unroll
     for (int m = 0; m < NM; m++) seg[m] = 0.0f;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float 
     float px = __fsub_rn(x, 1.0f), py = __fsub_rn(y, 1.0f), pz = __fsub_rn(z, 1.0f);  // K.cu:402-404
     float bx = floorf(px), by = floorf(py), bz = floorf(pz);
     int ci = min(max((int)bx + 2, 0), vol.ni), cj = min(max((int)by + 2, 0), vol.nj), ck = min(max((int)bz + 2, 0), vol.nk);
-    uint2 lab8 = __ldg(vol.celll + ((size_t)ck * (vol.nj + 1) + cj) * (vol.ni + 1) + ci);
+    uint2 lab8 = __ldg(vol.celll + ((unsigned)ck * (unsigned)(vol.nj + 1) + (unsigned)cj) * (unsigned)(vol.ni + 1) + (unsigned)ci);  // < 2^31 cells (drr_add_volume)
     float seg[NM];
 #pragma unroll
     for (int m = 0; m < NM; m++) seg[m] = 0.0f;
@@ -178,6 +178,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
     float cur = 0.0f;
     int live = -1;
     const int nxm = vol.ni - 2, nym = vol.nj - 2, nzm = vol.nk - 2;  // max cell base
+    const float sxm = sx - 1.0f, sym = sy - 1.0f, szm = sz - 1.0f;
 
     while (t < t_end) {
         // the march goes on to the far end of the farthest volume (K.cu:321-334); past this volume's window nothing is added
@@ -256,9 +257,9 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         for (;;) {
             float a1 = __fmaf_rn((float)S, step, alpha);
             bool part = (t < num_steps) && !(a1 < lo - 0.01f) && !(alpha > hi + 0.01f);
-            float p0x = __fmaf_rn(alpha, dx, sx) - 1.0f, p1x = __fmaf_rn(a1, dx, sx) - 1.0f;
-            float p0y = __fmaf_rn(alpha, dy, sy) - 1.0f, p1y = __fmaf_rn(a1, dy, sy) - 1.0f;
-            float p0z = __fmaf_rn(alpha, dz, sz) - 1.0f, p1z = __fmaf_rn(a1, dz, sz) - 1.0f;
+            float p0x = __fmaf_rn(alpha, dx, sxm), p1x = __fmaf_rn(a1, dx, sxm);  // p = x - 1 to within an ulp: a bound, the slack covers it
+            float p0y = __fmaf_rn(alpha, dy, sym), p1y = __fmaf_rn(a1, dy, sym);
+            float p0z = __fmaf_rn(alpha, dz, szm), p1z = __fmaf_rn(a1, dz, szm);
             // slack: the drift of the accumulated alpha against a1 (both sides) and, on the high side, the 1/512 by which a
             // sample's fixed-point coordinate can round up into the next cell
             int lx = max(-2, min(nxm, (int)floorf(fminf(p0x, p1x) - 0.01f))), hx = max(-2, min(nxm, (int)floorf(fmaxf(p0x, p1x) + 0.0125f)));
@@ -300,13 +301,19 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         int first_code = -1;
         bool same = true;
         {
-            const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
+            // e -> (cx, cy, cz) with multiply-shift divisions: m = trunc(65536 / n) + 2 overestimates 65536 / n by less than 3, so
+            // (e * m) >> 16 == e / n as long as 3 * e * n < 65536 (e < 2112 cells for the TEX sampler's code-only boxes, n <= e)
+            // ... which holds for e * n < 21845; larger boxes take the exact division
+            const unsigned mnx = (unsigned)(65536.0f / (float)nx) + 2u, mny = (unsigned)(65536.0f / (float)ny) + 2u;
+            const bool small_box = ncell * max(nx, ny) < 21845;
+            const unsigned row_stride = (unsigned)(vol.ni + 1), slice_stride = row_stride * (unsigned)(vol.nj + 1);
+            const unsigned cell0 = (unsigned)(blz + 2) * slice_stride + (unsigned)(bly + 2) * row_stride + (unsigned)(blx + 2);
             auto cell_of = [&](int e) {
-                int row = (int)(((float)e + 0.5f) * inv_nx);  // e / nx (exact for e < 2^16)
-                int cx = e - row * nx;
-                int cz = (int)(((float)row + 0.5f) * inv_ny);
-                int cy = row - cz * ny;
-                return ((size_t)(blz + cz + 2) * (vol.nj + 1) + (bly + cy + 2)) * (vol.ni + 1) + (blx + cx + 2);
+                unsigned row, cz;
+                if (small_box) { row = ((unsigned)e * mnx) >> 16; cz = (row * mny) >> 16; }
+                else { row = (unsigned)e / (unsigned)nx; cz = row / (unsigned)ny; }
+                const unsigned cx = (unsigned)e - row * (unsigned)nx, cy = row - cz * (unsigned)ny;
+                return cell0 + cz * slice_stride + cy * row_stride + cx;
             };
             if (STAGE_COEF) {
                 // all loads of the segment are put in flight at once: the 32 B records go global -> shared with
@@ -317,7 +324,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                     const int e = lane + 32 * k;
                     cc[k] = -1;
                     if (e < ncell) {
-                        const size_t cell = cell_of(e);
+                        const unsigned cell = cell_of(e);
                         cc[k] = __ldg(vol.cellcode + cell);
                         // the two 16 B halves of a record go to separate planes: consecutive cells then fall into
                         // distinct 16 B bank groups for the LDS.128 of the FMA-pipe sampler
