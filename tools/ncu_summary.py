@@ -23,7 +23,10 @@ h = rows[1]
 ie, src, at, ss = h.index("Instructions Executed"), h.index("Source"), h.index("Avg. Threads Executed"), h.index("# Samples")
 data = [(int(r[ie]), float(r[at]) if r[at] else 0, r[src].strip(), int(r[ss])) for r in rows[2:] if len(r) > ie]
 tot, tots = sum(d[0] for d in data), sum(d[3] for d in data)
-tex_lane_fetches = sum(d[0] * d[1] for d in data if (d[2].split()[1] if d[2].startswith("@") else d[2].split()[0]).startswith("TEX"))
+# fetches really issued: predicated-off lanes (e.g. mixed-label samples that reuse the group's fetch) do not count
+pon = h.index("Predicated-On Thread Instructions Executed")
+tex_lane_fetches = sum(int(r[pon]) for r in rows[2:] if len(r) > pon and r[src].strip() and
+                       (r[src].split()[1] if r[src].strip().startswith("@") else r[src].split()[0]).startswith("TEX"))
 print("texture fetches (lanes) %.4e" % tex_lane_fetches)
 print("total warp-inst %.3e" % tot, "n sass", len(data), "samples", tots)
 i = 0
