@@ -40,7 +40,7 @@ struct MarchParams {
     int V, M, W, H, n_views;
     float step, max_ray_length;
     int attenuate_outside, air_index;
-    int tex_eighths;  // hybrid sampler: how many of every 8 warps use the texture unit
+    int tex_eighths;  // hybrid sampler: how many of every 8 consecutive steps of a fast segment use the texture unit
     // meshes (K.cu:172-177); null when unused
     int mesh_layers, max_hits, n_mesh_mats;
     const float* hit_alphas;

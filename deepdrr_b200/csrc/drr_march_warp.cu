@@ -9,12 +9,16 @@
 // Here a warp owns an 8x4 pixel tile and walks its 32 rays in lock step over the global step index
 // t (all rays start at minAlpha ~ ray_length, so equal t means a coherent sample front).  For every
 // segment of <= SEG steps the warp
-//   1. bounds the voxel cells its rays will touch (two FMAs per lane + redux.sync min/max),
+//   1. bounds the voxel cells its rays will touch (two FMAs per lane and axis + redux.sync min/max),
 //   2. stages those cells once, cooperatively, into shared memory: the 32 B filter-coefficient
-//      record (ALU role only) and the 1 B label code of each cell (coalesced 128-bit loads),
-//   3. marches the segment out of shared memory with no divergence: one LDS.U8 (+ two LDS.128) per
-//      sample, the texture-unit arithmetic on the FMA pipes (ALU role) or one tex3D (TEX role).
-// Warps of both roles share every SM, so the TEX pipe and the FMA pipes are busy together.
+//      record (cp.async, two planes) and the 1 B label code of each cell,
+//   3. marches the segment out of shared memory with no divergence.  Where the whole box carries one
+//      label and every lane is inside its window, groups of 8 steps take 4 samples from the texture
+//      unit (tex3D) and 4 from the FMA pipes (the unit's arithmetic on the staged records; its 1.8
+//      fixed-point coordinate comes from one round-down FFMA per axis, the record index from two
+//      PRMT and a dp4a), so both resources are busy together; elsewhere groups of 4 steps look up
+//      their label codes and either add four fetched values or replay the steps one by one.
+// The sampler mix is a function of the step index only, so results do not depend on scheduling.
 #include <math_constants.h>
 
 #include <type_traits>
