@@ -258,6 +258,12 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         const int cap = STAGE_COEF ? MAXC : MAXC_TEX;
         int blx, bly, blz, nx, ny, nz;
         bool any;
+        // The staging index is built from one byte per axis and byte weights (dp4a): with the coefficient records the cap of
+        // MAXC <= 255 cells implies that; the code-only boxes of the TEX sampler (cap 33 * MAXC) have to ask for it.
+        auto box_fits = [&](int bx, int by, int bz) {
+            if (STAGE_COEF && MAXC <= 255) return bx * by * bz <= cap;
+            return bx * by * bz <= cap && max(bx, max(by, bz)) <= 255 && (bx * by <= 255 || bz == 1);
+        };
         for (;;) {
             float a1 = __fmaf_rn((float)S, step, alpha);
             bool part = (t < num_steps) && !(a1 < lo - 0.01f) && !(alpha > hi + 0.01f);
@@ -275,7 +281,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             any = bhx >= blx;
             if (!any) break;
             nx = bhx - blx + 1; ny = bhy - bly + 1; nz = bhz - blz + 1;
-            if (nx * ny * nz <= cap || S == 1) break;
+            if (box_fits(nx, ny, nz) || S == 1) break;
             S >>= 1;
         }
         if (!any) {  // nobody samples in this segment: just advance alpha
@@ -284,7 +290,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             continue;
         }
         const int ncell = nx * ny * nz;
-        if (ncell > cap) {
+        if (!box_fits(nx, ny, nz)) {
             // Even a single step of this tile does not fit the staging buffer (rays far apart compared with
             // the voxel size): take the generic per-sample path for this step.  Correct for any geometry;
             // the host picks the per-ray kernel for such set-ups (drr_capi.cu: pick_variant).

@@ -108,15 +108,22 @@ int main(void) {
         n_q++;
     }
 
-    /* 2. staging index from the cell bytes */
-    for (long it = 0; it < 400000; it++) {
-        int nx = 1 + rand() % 12, ny = 1 + rand() % 12, nz = 1 + rand() % 12;
-        if (nx * ny * nz > 256) continue;
+    /* 2. staging index from the cell bytes, for every box shape march_core's box_fits() lets through: up to 96 cells with the
+     * coefficient records, up to 33 * 96 code-only cells for the TEX sampler provided each side and nx * ny fit a byte */
+    long n_idx = 0;
+    for (long it = 0; it < 2000000; it++) {
+        int big = it & 1;
+        int nx = 1 + rand() % (big ? 300 : 12), ny = 1 + rand() % (big ? 300 : 12), nz = 1 + rand() % (big ? 40 : 12);
+        int cap = big ? 33 * 96 : 96;
+        int mx = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
+        int fits = big ? (nx * ny * nz <= cap && mx <= 255 && (nx * ny <= 255 || nz == 1)) : (nx * ny * nz <= cap);
+        if (!fits) continue;
         int cx = rand() % nx, cy = rand() % ny, cz = rand() % nz;
         uint32_t qx = 0x4B000000u | (cx << 8) | (rand() & 0xFF), qy = 0x4B000000u | (cy << 8) | (rand() & 0xFF), qz = 0x4B000000u | (cz << 8) | (rand() & 0xFF);
         uint32_t cell_w = 1u | ((uint32_t)(nx < 255 ? nx : 255) << 8) | ((uint32_t)(nx * ny < 255 ? nx * ny : 255) << 16);
         uint32_t idx = dp4a_u8(byte_perm(byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0);
         if (idx != (uint32_t)(cx + nx * (cy + ny * cz))) bad_idx++;
+        n_idx++;
     }
 
     /* 3. multiply-shift division of the staging loop (valid while e * n < 21845) */
@@ -182,7 +189,7 @@ int main(void) {
             if (fabsf(got - want) > 4.0f * ulp) { if (n_far < 5) printf("filter: got %.9g want %.9g (a,b,c)=(%d,%d,%d)\n", got, want, a, b, c); n_far++; }
         }
     }
-    printf("fixed-point coordinate: %ld cases, bad %ld, floor form bad %ld; index bad %ld; division bad %ld\n", n_q, bad_q, bad_floor, bad_idx, bad_div);
+    printf("fixed-point coordinate: %ld cases, bad %ld, floor form bad %ld; index: %ld boxes, bad %ld; division bad %ld\n", n_q, bad_q, bad_floor, n_idx, bad_idx, bad_div);
     printf("weights: all 256^3 x 2 slices, bad %ld\n", bad_w);
     printf("filter: %ld samples, bit-equal %.4f, beyond four ulps of the largest texel %ld\n", n_f, (double)n_eq / n_f, n_far);
     int ok = bad_q == 0 && bad_floor == 0 && bad_idx == 0 && bad_div == 0 && bad_w == 0 && n_far == 0 && n_eq > 0.5 * n_f;

@@ -28,5 +28,6 @@ def test_device_code_is_the_same_arithmetic():
         assert needle in body, needle
     march = open(os.path.join(ROOT, "deepdrr_b200", "csrc", "drr_march_warp.cu")).read()
     for needle in ("__fmaf_rn(-256.0f, b1x, 8388608.0f)", "__fadd_rn(kfx, 0.5f)", "__fmaf_rd(x, 256.0f, kqx)", "__fmaf_rd(x, 256.0f, kfx)",
-                   "__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510)", "(unsigned)(65536.0f / (float)nx) + 2u", "< 21845"):
+                   "__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510)", "(unsigned)(65536.0f / (float)nx) + 2u", "< 21845",
+                   "max(bx, max(by, bz)) <= 255 && (bx * by <= 255 || bz == 1)"):
         assert needle in march, needle
