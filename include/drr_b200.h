@@ -91,9 +91,10 @@ int drr_set_priorities(drr_ctx* ctx, const int* priority, const int* enabled, in
  * (projector.py:554-568, -D ATTENUATE_OUTSIDE_VOLUME / AIR_INDEX), sampler = DRR_SAMPLER_*. */
 int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int air_index, int sampler);
 
-/* Tuning knobs; results do not depend on them.
- *   DRR_TUNE_TEX_EIGHTHS    DRR_SAMPLER_HYBRID: how many of every 8 warps fetch density through the
- *                           texture unit (the rest emulate it on the FMA pipes), 0..8.
+/* Tuning knobs; results stay within the parity tolerance whatever they are set to.
+ *   DRR_TUNE_TEX_EIGHTHS    DRR_SAMPLER_HYBRID: how many of every 8 consecutive steps of a uniform segment fetch
+ *                           density through the texture unit (the rest emulate it on the FMA pipes); 0, 4 (default),
+ *                           5, 6, 7 or 8 (1..3 run as 4).
  *   DRR_TUNE_KERNEL_VARIANT single-volume march: 0 = warp-cooperative shared-memory staging (default),
  *                           1 = per-ray register cell cache. */
 #define DRR_TUNE_TEX_EIGHTHS 0
