@@ -107,3 +107,15 @@ def test_oracle_analytic_known_answers():
     r2 = cpu_oracle.project([v.data, v.data], st2.labels, st2.M, 16, 16, step, w2, s2, i2, mrl, e1, p1, mu1, priority=[0, 0])
     # (two half-weight additions per step round differently from one full-weight addition: 7e-6 over ~4 000 steps)
     assert np.max(np.abs(r2.area[soft] - L)) <= 2e-5 * float(L.max())
+
+
+@pytest.mark.parametrize("name", ["c1", "thorax_small"])
+def test_fma_pipe_sampler_arithmetic_matches_reference_kernel(name):
+    """The float form the CUDA FMA-pipe sampler evaluates (fixed-point coordinate from a round-down FMA, magic-number weight
+    splits, FMA chain over the per-cell records; oracle tex_mode 3) marched through the oracle with EVERY sample taken this way:
+    same goldens, same tolerance.  Measured: thorax_small 3.7e-7; c1 9.8e-6 on one pixel whose air total is a few near-zero
+    samples (the sensitivity DESIGN.md section 2 describes for the texture-less `alu` sampler; the float form it replaced gave
+    9.6e-6 there, the integer model 3.4e-7).  The default hybrid sampler takes at most half of a ray's samples this way."""
+    line, inten = _check_case(name, views=[0], tex_mode=3)
+    assert line <= LINE_RTOL, f"{name}: line integrals off by {line:.2e}"
+    assert inten <= INT_RTOL, f"{name}: intensity off by {inten:.2e}"
