@@ -113,9 +113,10 @@ def test_oracle_analytic_known_answers():
 def test_fma_pipe_sampler_arithmetic_matches_reference_kernel(name):
     """The float form the CUDA FMA-pipe sampler evaluates (fixed-point coordinate from a round-down FMA, magic-number weight
     splits, FMA chain over the per-cell records; oracle tex_mode 3) marched through the oracle with EVERY sample taken this way:
-    same goldens, same tolerance.  Measured: thorax_small 3.7e-7; c1 9.8e-6 on one pixel whose air total is a few near-zero
-    samples (the sensitivity DESIGN.md section 2 describes for the texture-less `alu` sampler; the float form it replaced gave
-    9.6e-6 there, the integer model 3.4e-7).  The default hybrid sampler takes at most half of a ray's samples this way."""
+    same goldens, same tolerance.  Measured: thorax_small 3.7e-7; c1 9.8e-6, on one pixel whose air total comes from a few
+    mixed-label samples with tiny weights (the float form it replaced gave 9.6e-6 there, the integer model 3.4e-7).  This is
+    stricter than the product: the kernels use this form in uniform-label cells only and send mixed-label samples through the
+    texture unit, which is why the GPU's all-ALU run of c1 stays at 4.7e-7."""
     line, inten = _check_case(name, views=[0], tex_mode=3)
     assert line <= LINE_RTOL, f"{name}: line integrals off by {line:.2e}"
     assert inten <= INT_RTOL, f"{name}: intensity off by {inten:.2e}"
