@@ -120,3 +120,12 @@ def test_fma_pipe_sampler_arithmetic_matches_reference_kernel(name):
     line, inten = _check_case(name, views=[0], tex_mode=3)
     assert line <= LINE_RTOL, f"{name}: line integrals off by {line:.2e}"
     assert inten <= INT_RTOL, f"{name}: intensity off by {inten:.2e}"
+
+
+@pytest.mark.parametrize("name", ["c1", "thorax_small"])
+def test_fma_pipe_sampler_with_the_kernels_selection(name):
+    """The same float form applied the way the kernels apply it (oracle tex_mode 4): in cells whose eight labels agree; mixed-label
+    samples through the texture unit's integer model.  c1 comes out at 3.57e-7 -- the figure the GPU's `alu` sampler measures."""
+    line, inten = _check_case(name, views=[0], tex_mode=4)
+    assert line <= 1e-6, f"{name}: line integrals off by {line:.2e}"
+    assert inten <= INT_RTOL
