@@ -10,9 +10,9 @@ data-path collective; weak scaling.  Prints ONE JSON line on ra
 
 value  = views / s with volumes resident in HBM and images left in device memory (CUDA events on the
          stream the kernels run on, max over ranks).
-e2e    = same through the public API call a user makes (Projector.project on host pose objects ->
-         host images): per-view pose arrays H2D, kernels, images D2H into pinned memory, inside the
-         timed region.
+e2e    = same through the public API call a user makes, ``images = projector.project(*poses)`` on host pose
+         objects -> host images: pose math, pose upload, kernels, images D2H (into the projector's page-locked
+         result pool), all inside the timed region.
 --impl reference times the reference's own unmodified CUDA kernel (oracle/_ref, compiled from
 /root/reference by oracle/Makefile) driven the way the reference's Python drives it: per view five
 small H2D uploads, one launch, two blocking D2H copies, two host transposes, host neglog
@@ -48,7 +48,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -61,12 +61,53 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+                self.proc.wait()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
+
+
+_PROBE = ("import ctypes,sys\nl=ctypes.CDLL('libcuda.so.1')\nr=l.cuInit(0)\nn=ctypes.c_int(0)\nr2=l.cuDeviceGetCount(ctypes.byref(n)) if r==0 else -1\n"
+          "print(r,r2,n.value)\nsys.exit(0 if (r==0 and r2==0 and n.value>0) else 3)")
+
+
+def _wait_for_cuda(max_wait_s=150.0):
+    """Bounded wait until a fresh process can initialise CUDA.  The driver starts this script seconds after another GPU
+    process (the reference arm) has exited; a GPU that is still tearing down / re-initialising then fails cuInit once and
+    PyTorch caches that failure for the life of the process -- so the probe runs in a child and is retried."""
+    t0, last = time.time(), ""
+    while True:
+        try:
+            r = subprocess.run([sys.executable, "-c", _PROBE], capture_output=True, text=True, timeout=60)
+            last = (r.stdout + r.stderr).strip()[-300:]
+            if r.returncode == 0:
+                return True, last, time.time() - t0
+        except Exception as e:  # probe hung or could not start
+            last = repr(e)[:300]
+        if time.time() - t0 > max_wait_s:
+            return False, last, time.time() - t0
+        time.sleep(3.0)
+
+
+def _cuda_or_die(args, impl):
+    ok, last, waited = _wait_for_cuda()
+    if ok:
+        return waited
+    smi = ""
+    try:
+        smi = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.strip()[:300]
+    except Exception as e:
+        smi = repr(e)[:200]
+    print(json.dumps({"impl": impl, "error": "CUDA did not initialise within the bounded wait", "waited_s": round(waited, 1),
+                      "probe": last, "nvidia_smi_L": smi, "n_gpus": args.gpus}), flush=True)
+    sys.exit(1)
 
 
 def _dist_setup(n_gpus):
@@ -125,15 +166,15 @@ def _peaks():
 
 
 def _ncu_capture():
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_bench_ncu.json")))
-    except Exception:
-        return {}
-
-
-def _ncu_traffic():
-    """DRAM bytes per launch of the march kernel from the committed ncu capture of this command, if any."""
-    return _ncu_capture().get("march_dram_bytes_per_launch")
+    """The newest committed ncu summary of this command (profiles/rNN_bench_ncu.json, written by tools/ncu_summary.py)."""
+    for name in ("r02_bench_ncu.json", "r01_bench_ncu.json"):
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+            cap["_file"] = "profiles/" + name
+            return cap
+        except Exception:
+            continue
+    return {}
 
 
 def cpu_baseline_port(volume, st, carm, pose, crop=256):
@@ -183,6 +224,7 @@ def secondary_configs(ct, device, sampler, n_views=16):
 
 
 def run_ours(args):
+    waited = _cuda_or_die(args, "ours")
     import torch
 
     from deepdrr_b200 import Projector, geo, phantoms
@@ -201,29 +243,30 @@ def run_ours(args):
     p.initialize()
     stream = torch.cuda.current_stream()
     p.set_stream(stream.cuda_stream)
-    p.max_ray_length = carm.max_ray_length
+    mrl = carm.max_ray_length
 
     def step_poses(s):
         base = (s * world + rank) * B
         return [poses[(base + i) % n_pose] for i in range(B)]
 
-    # ---- device-resident throughput ("value") ------------------------------------------------------
+    # ---- device-resident throughput ("value"): kernel-level pose arrays in, images left in HBM ---------
     out_dev = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
-    arrays = [p._pose_arrays(step_poses(s)) for s in range(args.warmup + args.steps)]
+    arrays = [geo.pose_arrays_batch(step_poses(s), [volume]) for s in range(args.warmup + args.steps)]
     for s in range(args.warmup):
-        p._run(*arrays[s], W, H, "intensity", out_dev, False, None)
+        p.project_arrays(*arrays[s], (W, H), mrl, want="intensity", out=out_dev)
     launches0 = p.launch_count()
     clocks = ClockSampler(local)
     _barrier(world)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    march_ms, samples = [], 0
+    march_ms, steps_total, window_total = [], 0, 0
     e0.record(stream)
     for s in range(args.warmup, args.warmup + args.steps):
-        p._run(*arrays[s], W, H, "intensity", out_dev, False, None)
+        p.project_arrays(*arrays[s], (W, H), mrl, want="intensity", out=out_dev)
         march_ms.append(p.last_timing_ms()["march"])
-        samples += p.last_sample_count()
+        steps_total += p.last_sample_count()
+        window_total += p.last_window_samples()
     e1.record(stream)
     _barrier(world)
     dev_ms = _max_over_ranks(e0.elapsed_time(e1), world)
@@ -231,23 +274,21 @@ def run_ours(args):
     total_views = B * args.steps * world
     value = total_views / (dev_ms * 1e-3)
 
-    # ---- end to end through the public API ("e2e") -------------------------------------------------
-    pinned = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-    out_host = pinned.numpy()
-    for s in range(min(args.warmup, 2)):
-        p._project_batch(step_poses(s), want="intensity", out=out_host)
+    # ---- end to end through the public API ("e2e"): images = projector.project(*poses) -------------------
+    for s in range(min(args.warmup, 3)):
+        img = p.project(*step_poses(s), max_ray_length=mrl)
     _barrier(world)
     t0 = time.perf_counter()
-    checksum = 0.0
+    checksum = None
     for s in range(args.warmup, args.warmup + args.steps):
-        p.max_ray_length = carm.max_ray_length
-        img = p._project_batch(step_poses(s), want="intensity", out=out_host)  # what Projector.project does, into pinned memory
-        checksum += float(img[0, H // 2, W // 2])
+        img = p.project(*step_poses(s), max_ray_length=mrl)      # host poses in, host [B, H, W] images out
+        if checksum is None:
+            checksum = float(np.mean(img[0], dtype=np.float64))   # same definition on the reference arm: its first timed view
     _barrier(world)
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     e2e_value = total_views / e2e_s
     clk = clocks.stop() if rank == 0 else None
-    h2d = B * (9 + 3 + 12) * 4
+    h2d = B * (9 + 3 + 12 + 9) * 4                               # one ViewDev record per view (poses + inverse matrix)
     d2h = B * H * W * 4
 
     # ---- roofline of the dominant kernel (ray march) ------------------------------------------------
@@ -255,14 +296,19 @@ def run_ours(args):
     bytes_view = SHAPE[0] * SHAPE[1] * SHAPE[2] * 5 + W * H * 8          # 543 162 368 B
     avg_march_s = float(np.mean(march_ms)) * 1e-3
     achieved = bytes_view * B / avg_march_s / 1e9
-    samples_per_s = _sum_over_ranks(samples / (sum(march_ms) * 1e-3), world)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": _ncu_traffic(), "kernel": "march_warp_kernel", "peak_source": peak_src,
-                "note": "the march is a cache-resident gather (issue / TEX bound), so the HBM fraction is small by construction (SURVEY.md 8(d)); "
-                        "binding-resource figures are in 'binding'"}
-    binding = {"ray_steps_per_s": samples_per_s, "march_ms_per_view": float(np.mean(march_ms)) / B,
-               "steps_per_view": samples / (B * args.steps), "gather_GBps_at_40B_per_step": samples_per_s * 40 / 1e9}
+    march_s_total = sum(march_ms) * 1e-3
+    window_per_s = _sum_over_ranks(window_total / march_s_total, world)
     cap = _ncu_capture()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": cap.get("march_dram_bytes_per_launch"), "traffic_source": cap.get("_file"),
+                "kernel": "march_warp_kernel", "peak_source": peak_src,
+                "note": "the march is a cache-resident gather (TEX / issue bound), so the HBM fraction is small by construction (SURVEY.md 8(d)); "
+                        "binding-resource figures are in 'binding'"}
+    binding = {"march_ms_per_view": float(np.mean(march_ms)) / B,
+               "march_steps_per_view": steps_total / (B * args.steps),            # all steps the reference takes (K.cu:334), incl. the empty ones
+               "window_samples_per_view": window_total / (B * args.steps),        # steps inside the volume: the samples that fetch density
+               "window_samples_per_s": window_per_s,
+               "gather_GBps_at_40B_per_sample": window_per_s * 40 / 1e9}
     if cap.get("tex_lane_fetches_per_launch"):
         # texture-unit load: fetches per view counted by ncu (SASS TEX instructions x active lanes) x views/s, against the unit's
         # measured peak of 1.98 trilinear fp32 fetches / clk / SM (tools/tex_rate.cu on a B200: 5.5e11 /s)
@@ -271,28 +317,32 @@ def run_ours(args):
         binding["tex_fetches_per_s"] = rate
         binding["tex_peak_fetches_per_s"] = 5.5e11
         binding["tex_frac_of_peak"] = rate / 5.5e11
-    if cap:  # what actually binds, from the committed ncu capture of this command (profiles/r01_bench_ncu.json)
-        binding["ncu_capture"] = {k: cap.get(k) for k in ("issue_slot_utilisation", "tex_request_cycles_pct", "pipe_fma_pct", "pipe_alu_pct",
-                                                          "shared_pipe_wavefronts_pct", "avg_active_lanes", "l1tex_hit_pct", "l2_hit_pct",
-                                                          "warps_active_pct", "registers_per_thread")}
+    if cap:  # what binds, from the committed ncu capture of this command (stale if the kernel changed since: see its "head")
+        binding["from_committed_capture"] = {k: cap.get(k) for k in ("_file", "head", "kernel", "issue_slot_utilisation", "tex_request_cycles_pct", "pipe_fma_pct",
+                                                                     "pipe_alu_pct", "shared_pipe_wavefronts_pct", "avg_active_lanes", "l1tex_hit_pct",
+                                                                     "l2_hit_pct", "warps_active_pct", "registers_per_thread")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is reported at N = 1 only
         st = SceneTables([volume], SPECTRUM)
-        cpu = cpu_baseline_port(volume, st, carm, poses[0])
+        cpu = cpu_baseline_port(volume, st, carm, poses[0], crop=args.cpu_crop)
+    del img
     p.free()
     secondary = None
-    if rank == 0 and world == 1 and not args.no_secondary:
+    if rank == 0 and world == 1 and args.secondary:
         secondary = secondary_configs(volume, local, args.sampler)
     if rank == 0:
         line = {"metric": "DRRs/s", "value": value, "unit": "DRRs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "rays_per_s": value * W * H,
-                "config": {"workload": WORKLOAD, "views_per_step_per_gpu": B, "sensor": [W, H], "volume": list(SHAPE), "step_mm": STEP_MM,
-                           "sampler": args.sampler, "cache": "inputs larger than L2 (4.2 GB of cell records + 0.5 GB volume per GPU)",
+                "config": {"workload": WORKLOAD, "views_per_step_per_gpu": B, "views_total": total_views, "sensor": [W, H], "volume": list(SHAPE),
+                           "step_mm": STEP_MM, "sampler": args.sampler,
+                           "cache": "inputs larger than L2 (4.2 GB of cell records + 0.5 GB volume per GPU)",
                            "parallelism": f"views sharded over {world} GPU(s), volume replicated, no collective"},
-                "e2e": {"value": e2e_value, "unit": "DRRs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "checksum": checksum},
-                "gpu_launches": int(launches), "roofline": roofline, "binding": binding, "cpu_baseline": cpu, "clocks": clk}
+                "e2e": {"value": e2e_value, "unit": "DRRs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "call": "Projector.project(*poses) -> host ndarray"},
+                "checksum": checksum, "gpu_launches": int(launches), "roofline": roofline, "binding": binding, "cpu_baseline": cpu, "clocks": clk,
+                "cuda_init_wait_s": round(waited, 1)}
         if secondary is not None:
             line["secondary"] = secondary
         print(json.dumps(line), flush=True)
@@ -306,9 +356,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the reference arm
+    from oracle import ref_gpu
+
+    have_gpu_ref = ref_gpu.available()
+    if have_gpu_ref:
+        ok, _, _ = _wait_for_cuda(60.0)
+        have_gpu_ref = ok
     from deepdrr_b200 import geo, phantoms
     from deepdrr_b200.scene import SceneTables
-    from oracle import ref_gpu
 
     B = args.views_per_step
     carm = phantoms.MobileCArmGeometry()
@@ -316,15 +371,8 @@ def run_reference(args):
     volume = phantoms.thorax_volume(SHAPE, SPACING)
     st = SceneTables([volume], SPECTRUM)
     poses = phantoms.c2_poses(1000, seed=1, carm=carm)
-    config = {"workload": WORKLOAD, "views_per_step_per_gpu": B, "sensor": [W, H], "volume": list(SHAPE), "step_mm": STEP_MM}
-    have_gpu_ref = ref_gpu.available()
-    if have_gpu_ref:
-        try:
-            import torch
-
-            have_gpu_ref = torch.cuda.is_available()
-        except Exception:
-            have_gpu_ref = False
+    config = {"workload": WORKLOAD, "views_per_step_per_gpu": B, "views_total": B * args.steps, "sensor": [W, H], "volume": list(SHAPE),
+              "step_mm": STEP_MM}
     if have_gpu_ref:
         ref = ref_gpu.RefProjector([volume.data], st.labels, st.M, [volume.spacing])
         ref.set_spectrum(st.energies, st.pdf, st.mu)
@@ -352,8 +400,11 @@ def run_reference(args):
         kernel_ms.clear()
         clocks.start()
         t0 = time.perf_counter()
+        checksum = None
         for s in range(args.warmup, args.warmup + args.steps):
             out = one_step(s)
+            if checksum is None:
+                checksum = float(np.mean(out[0], dtype=np.float64))                   # first timed view, as on the other arm
         dt = time.perf_counter() - t0
         clk = clocks.stop()
         value = B * args.steps / dt
@@ -365,9 +416,9 @@ def run_reference(args):
                                            "reference's per-view host flow on one host thread -- the reference has no CPU implementation of this path"},
                 "e2e": {"value": value, "unit": "DRRs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "reference_kernel_ms_per_view": float(np.mean(kernel_ms)), "reference_kernel_only_DRRs_per_s": 1e3 / float(np.mean(kernel_ms)),
-                "clocks": clk, "checksum": float(out[0, H // 2, W // 2])}
+                "clocks": clk, "checksum": checksum}
         ref.close()
-        if not args.no_secondary:
+        if args.secondary:
             try:  # the reference kernel on config 3 (CT + two K-wire volumes, 384x384); config 4 needs its OpenGL renderer
                 vols = phantoms.c3_scene(ct=volume)
                 st3 = SceneTables(vols, SPECTRUM)
@@ -384,6 +435,7 @@ def run_reference(args):
                 line["secondary"] = {"C3 CT + 2 K-wire volumes": {"views": len(ms3), "sensor": [384, 384], "reference_kernel_ms_per_view": float(np.mean(ms3))}}
             except Exception as e:  # a missing (V, M) cubin must not break the headline line
                 line["secondary"] = {"error": str(e)[:200]}
+        ref_gpu.shutdown()                                                            # everything freed and the device idle before the next arm starts
         print(json.dumps(line), flush=True)
         return
     # no reference cubin (or no GPU): time the CPU oracle port on a bounded sample per step
@@ -409,7 +461,9 @@ def main():
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--sampler", default="hybrid", choices=["hybrid", "alu", "tex"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 timings appended under 'secondary'")
+    ap.add_argument("--secondary", action="store_true", help="append C3 / C4 timings under 'secondary' (extra projectors after the headline run)")
+    ap.add_argument("--no-secondary", action="store_true", help="accepted for compatibility (the default now)")
+    ap.add_argument("--cpu-crop", type=int, default=512, help="side of the centred pixel crop the CPU oracle marches for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

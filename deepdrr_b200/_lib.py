@@ -27,7 +27,7 @@ MAX_VOLUMES, MAX_MATERIALS = 8, 16
 SYMBOLS = [
     "drr_create", "drr_destroy", "drr_last_error", "drr_set_stream", "drr_set_spectrum", "drr_add_volume", "drr_add_volume_hu",
     "drr_clear_volumes", "drr_set_priorities", "drr_set_march", "drr_set_tuning", "drr_set_mesh_buffers", "drr_set_meshes", "drr_set_mesh_poses", "drr_mesh_clean_hits", "drr_mesh_query", "drr_set_scatter_tables", "drr_scatter", "drr_postprocess",
-    "drr_project", "drr_last_timing", "drr_last_sample_count", "drr_launch_count", "drr_synchronize", "drr_version",
+    "drr_project", "drr_last_timing", "drr_last_sample_count", "drr_last_window_samples", "drr_host_alloc", "drr_host_free", "drr_launch_count", "drr_synchronize", "drr_version",
 ]
 
 _lib = None
@@ -71,6 +71,9 @@ def load() -> ctypes.CDLL:
     lib.drr_project.argtypes = [vp, ci, ci, ci, vp, vp, vp, cf, cu, cf, cf, cf, ctypes.c_uint64, vp, vp, vp, ci]
     lib.drr_last_timing.argtypes = [vp, vp]
     lib.drr_last_sample_count.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.drr_last_window_samples.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.drr_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.drr_host_free.argtypes = [vp]
     lib.drr_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
     lib.drr_synchronize.argtypes = [vp]
     _lib = lib

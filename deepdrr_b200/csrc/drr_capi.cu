@@ -231,7 +231,7 @@ struct drr_ctx {
     unsigned int* d_tile_counter = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[3] = {0, 0, 0};
-    unsigned long long last_samples = 0, launches = 0;
+    unsigned long long last_samples[2] = {0, 0}, launches = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -300,7 +300,7 @@ int drr_create(int device_id, drr_ctx** out) {
     CU(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (int i = 0; i < 5; i++) CU(nullptr, cudaEventCreate(&c->ev[i]));
-    CU(nullptr, cudaMalloc(&c->d_samples, sizeof(unsigned long long)));
+    CU(nullptr, cudaMalloc(&c->d_samples, 2 * sizeof(unsigned long long)));  // [0] march steps, [1] steps inside a volume window
     CU(nullptr, cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
     for (int i = 0; i < DRR_MAX_VOLUMES; i++) { c->priority[i] = 0; c->enabled[i] = 1; }
     *out = c;
@@ -859,7 +859,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     if ((rc = ensure(c, (void**)&c->d_area, &c->area_cap, sizeof(float) * npix * M * n_views))) return rc;
     if ((rc = ensure(c, (void**)&c->d_intensity, &c->int_cap, sizeof(float) * npix * n_views))) return rc;
     if ((rc = ensure(c, (void**)&c->d_pprob, &c->pp_cap, sizeof(float) * npix * n_views))) return rc;
-    CU(c, cudaMemsetAsync(c->d_samples, 0, sizeof(unsigned long long), s));
+    CU(c, cudaMemsetAsync(c->d_samples, 0, 2 * sizeof(unsigned long long), s));
     CU(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), s));
 
     MarchParams P;
@@ -1011,7 +1011,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     if (out_intensity) CU(c, cudaMemcpyAsync(out_intensity, c->d_intensity, sizeof(float) * npix * n_views, kind, s));
     if (out_pprob && out_intensity) CU(c, cudaMemcpyAsync(out_pprob, c->d_pprob, sizeof(float) * npix * n_views, kind, s));
     if (out_area) CU(c, cudaMemcpyAsync(out_area, c->d_area, sizeof(float) * npix * M * n_views, kind, s));
-    CU(c, cudaMemcpyAsync(&c->last_samples, c->d_samples, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->last_samples, c->d_samples, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CU(c, cudaEventRecord(c->ev[4], s));
     CU(c, cudaStreamSynchronize(s));
     CU(c, cudaEventElapsedTime(&c->last_ms[0], c->ev[1], c->ev[2]));
@@ -1071,7 +1071,25 @@ int drr_last_timing(const drr_ctx* c, float* ms3) {
 
 int drr_last_sample_count(const drr_ctx* c, unsigned long long* samples) {
     if (!c || !samples) return DRR_E_INVALID;
-    *samples = c->last_samples;
+    *samples = c->last_samples[0];
+    return DRR_OK;
+}
+
+int drr_last_window_samples(const drr_ctx* c, unsigned long long* samples) {
+    if (!c || !samples) return DRR_E_INVALID;
+    *samples = c->last_samples[1];
+    return DRR_OK;
+}
+
+int drr_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(nullptr, DRR_E_INVALID, "drr_host_alloc: bad arguments");
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; return fail(nullptr, DRR_E_NOMEM, "drr_host_alloc: %s", cudaGetErrorString(e)); }
+    return DRR_OK;
+}
+
+int drr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
     return DRR_OK;
 }
 

@@ -527,7 +527,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
 // Single-volume tile: per-lane ray set-up (K.cu:220-334), then the lock-step march.
 template <int NM, int KTEX>
 __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
-                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps) {
+                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps, unsigned long long& my_window) {
     const VolDev& vol = P.vol[0];
     float dx = 0.f, dy = 0.f, dz = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f;
     const float sx = vw.src[0][0], sy = vw.src[0][1], sz = vw.src[0][2];
@@ -543,6 +543,8 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
         }
     }
     my_steps += (unsigned)num_steps;
+    if (num_steps > 0 && hi >= lo)  // samples that fetch density: the steps whose alpha lies in [lo, hi] (to within one step)
+        my_window += (unsigned)min(num_steps, (int)__fdiv_rn(__fsub_rn(hi, fmaxf(lo, alpha)), P.step) + 1);
     march_core<NM, KTEX, false>(vol, P.step, sx, sy, sz, dx, dy, dz, lo, hi, alpha, num_steps, s_coef, s_code, lane, acc);
 }
 
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
     const size_t npix = (size_t)P.W * P.H;
     const float step = P.step;
-    unsigned long long my_steps = 0;
+    unsigned long long my_steps = 0, my_window = 0;
     for (;;) {
         unsigned tile = 0;
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
@@ -574,13 +576,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
         float acc[NM];
         const ViewDev& vw = P.views[view];
         switch (P.tex_eighths) {
-            case 0: march_tile<NM, 0>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
+            case 0: march_tile<NM, 0>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
             case 1: case 2: case 3:
-            case 4: march_tile<NM, 4>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
-            case 5: march_tile<NM, 5>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
-            case 6: march_tile<NM, 6>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
-            case 7: march_tile<NM, 7>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps); break;
-            default: march_tile<NM, 8>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps); break;
+            case 4: march_tile<NM, 4>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 5: march_tile<NM, 5>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 6: march_tile<NM, 6>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 7: march_tile<NM, 7>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            default: march_tile<NM, 8>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps, my_window); break;
         }
         if (ok) {
             float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
@@ -588,8 +590,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
             for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[m], step), 10.0f);  // K.cu:565-567, 582-584
         }
     }
-    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    if (lane == 0 && my_steps) atomicAdd(P.sample_count, my_steps);
+    for (int o = 16; o > 0; o >>= 1) {
+        my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+        my_window += __shfl_xor_sync(0xffffffffu, my_window, o);
+    }
+    if (lane == 0 && my_steps) { atomicAdd(P.sample_count, my_steps); atomicAdd(P.sample_count + 1, my_window); }
 }
 
 // ---------------------------------------------------------------------------------------------

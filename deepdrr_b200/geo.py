@@ -214,18 +214,36 @@ class CameraProjection:
         return -e[:3, :3].T @ e[:3, 3]
 
 
-def pose_arrays(proj, volumes: Sequence) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Per-view kernel inputs exactly as the reference derives them (projector.py:802-831).
+def pose_arrays_batch(projs: Sequence, volumes: Sequence) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Per-view kernel inputs for a batch of views, exactly as the reference derives them one view at a time
+    (projector.py:802-831): ``world_from_index`` (n, 9) f32, ``source_ijk`` (n, V, 3) f32, ``ijk_from_world`` (n, V, 12) f32.
 
-    Returns ``world_from_index`` (9,) f32, ``source_ijk`` (V,3) f32, ``ijk_from_world`` (V,12) f32.
+    All views go through stacked float64 NumPy operations (no per-view Python loop for this module's own
+    ``CameraProjection``); foreign projection objects (killeengeo) are read through their ``world_from_index`` /
+    ``center_in_world`` properties.  ``pose_arrays`` is this function with n = 1, so both give identical bits.
     """
-    w2i = np.array(np.asarray(proj.world_from_index)[:-1, :]).astype(np.float32).reshape(9)
-    c = np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3]
-    src = np.zeros((len(volumes), 3), dtype=np.float32)
-    a = np.zeros((len(volumes), 12), dtype=np.float32)
+    n, V = len(projs), len(volumes)
+    if n and all(type(p) is CameraProjection for p in projs):
+        e = np.stack([p.camera3d_from_world.data for p in projs])                 # (n, 4, 4)
+        k = np.stack([p.index_from_camera2d.data for p in projs])                 # (n, 3, 3)
+        rt = np.transpose(e[:, :3, :3], (0, 2, 1))
+        w64 = rt @ np.linalg.inv(k)                                               # world_from_index[:3] = R^T K^-1
+        c = -(rt @ e[:, :3, 3:4])[:, :, 0]                                        # center_in_world = -R^T t
+    else:
+        w64 = np.stack([np.asarray(p.world_from_index, dtype=np.float64)[:-1, :] for p in projs]) if n else np.zeros((0, 3, 3))
+        c = np.stack([np.asarray(p.center_in_world, dtype=np.float64).reshape(-1)[:3] for p in projs]) if n else np.zeros((0, 3))
+    w2i = np.ascontiguousarray(w64.astype(np.float32).reshape(n, 9))
+    src = np.zeros((n, V, 3), dtype=np.float32)
+    a = np.zeros((n, V, 12), dtype=np.float32)
     for i, v in enumerate(volumes):
         t = v.IJK_from_world
         m = np.asarray(t.toarray() if hasattr(t, "toarray") else t, dtype=np.float64)[:3, :]
-        src[i] = (m[:, :3] @ c + m[:, 3]).astype(np.float32)
-        a[i] = m.astype(np.float32).reshape(12)
+        src[:, i, :] = (c @ m[:, :3].T + m[:, 3]).astype(np.float32)
+        a[:, i, :] = m.astype(np.float32).reshape(12)
     return w2i, src, a
+
+
+def pose_arrays(proj, volumes: Sequence) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """One view: ``world_from_index`` (9,) f32, ``source_ijk`` (V, 3) f32, ``ijk_from_world`` (V, 12) f32."""
+    w2i, src, a = pose_arrays_batch([proj], volumes)
+    return w2i[0], src[0], a[0]

@@ -22,6 +22,7 @@ from typing import List, Optional, Sequence, Union
 import numpy as np
 
 from . import _lib, geo, vol
+from ._pinned import PinnedPool
 from .material import Material
 from .scene import default_priorities, material_universe, remap_labels
 from .spectral_data import get_spectrum, spectrum_tables
@@ -70,6 +71,7 @@ class Projector(object):
         sampler: str = "hybrid",
         noise_seed: Optional[int] = None,
         coefficient_records: bool = True,
+        pinned_output: bool = True,
     ) -> None:
         """See the reference docstring (projector.py:423-454).  Extra, optional arguments:
 
@@ -77,6 +79,9 @@ class Projector(object):
         noise_seed: seed of the Philox stream used by ``add_noise`` (the reference uses unseeded NumPy).
         coefficient_records: False skips the 32 B / voxel filter-coefficient records of the FMA-pipe sampler (the library
             does so by itself when they do not fit in device memory); the texture unit then fetches every sample.
+        pinned_output: the arrays ``project`` returns live in page-locked host memory taken from a small pool (full-rate
+            device-to-host copies; the block is recycled when the array is garbage collected).  At most 2 GiB are pinned
+            by live results; beyond that, and with False, plain ``np.empty`` arrays are returned as in the reference.
         """
         self.cuda_device_id = cuda_device_id
         self.mesh_layers = mesh_layers
@@ -166,6 +171,7 @@ class Projector(object):
         self.noise_seed = noise_seed
         self.coefficient_records = bool(coefficient_records)
         self._noise_calls = 0
+        self._pool = PinnedPool() if pinned_output else None
 
         self.output_shape = None
         self.initialized = False
@@ -276,6 +282,9 @@ class Projector(object):
         if self.initialized and self._h is not None:
             _lib.load().drr_destroy(self._h)
             self._h = None
+            if self._pool is not None:
+                self._pool.close()
+                self._pool = PinnedPool(self._pool.max_outstanding_bytes, self._pool.keep_free)
         self.initialized = False
 
     def __enter__(self):
@@ -309,18 +318,22 @@ class Projector(object):
             self.max_ray_length = self.source_to_detector_distance * 4
         return list(camera_projections)
 
-    def project(self, *camera_projections, max_ray_length: Optional[float] = None) -> np.ndarray:
+    def project(self, *camera_projections, max_ray_length: Optional[float] = None, out=None) -> np.ndarray:
         """Project every given view; returns ``[H, W]`` for one view, ``[N, H, W]`` otherwise (float32).
 
-        Reference: :655-707.  ``max_ray_length`` (extra) overrides the value derived at :641-650.
+        Reference: :655-707.  Extra keywords: ``max_ray_length`` overrides the value derived at :641-650; ``out`` is a
+        C-contiguous float32 ``[N, H, W]`` NumPy array (host; ideally page-locked) or CUDA tensor that receives the images.
         """
         camera_projections = self._prepare_project(camera_projections)
         if max_ray_length is not None:
             self.max_ray_length = float(max_ray_length)
         if self.scatter_num > 0:
             images = self._project_with_scatter(camera_projections)
+            if out is not None:
+                out[...] = images
+                images = out
         else:
-            images = self._project_batch(camera_projections, want="intensity")
+            images = self._project_batch(camera_projections, want="intensity", out=out)
         if images.shape[0] == 1:
             return images[0]
         return images
@@ -338,6 +351,8 @@ class Projector(object):
                 rank, world = dist.get_rank(), dist.get_world_size()
         except Exception:
             pass
+        if self.collected_energy:
+            raise ValueError("collected_energy is not available together with scatter_num > 0")
         images, pprob = self._project_batch(camera_projections, want="intensity+photon_prob")
         n = int(self.scatter_num)
         self.last_scatter_counters = []
@@ -352,7 +367,7 @@ class Projector(object):
         if flags:
             H, W = images.shape[1:]
             _lib.check(_lib.load().drr_postprocess(self._h, _lib.ptr(images), _lib.ptr(pprob), images.shape[0], W, H, flags, float(self.photon_count),
-                                                   float(self.intensity_upper_bound or 0.0), int(self.noise_seed or 0), _lib.MEM_HOST), self._h)
+                                                   float(self.intensity_upper_bound or 0.0), self._next_noise_seed(), _lib.MEM_HOST), self._h)
         return images
 
     def project_line_integrals(self, *camera_projections, max_ray_length: Optional[float] = None) -> np.ndarray:
@@ -382,16 +397,17 @@ class Projector(object):
         return self._run(w2i, src, ijk, int(sensor_size[0]), int(sensor_size[1]), want, out, raw, None, source_world)
 
     def _pose_arrays(self, camera_projections):
-        n, V = len(camera_projections), len(self.volumes)
-        w2i = np.zeros((n, 9), dtype=np.float32)
-        src = np.zeros((n, max(V, 1), 3), dtype=np.float32)
-        ijk = np.zeros((n, max(V, 1), 12), dtype=np.float32)
-        for i, proj in enumerate(camera_projections):
-            a, b, c = geo.pose_arrays(proj, self.volumes)
-            w2i[i] = a
-            if V:
-                src[i], ijk[i] = b, c
+        """Kernel-level arrays of a batch of views (reference :802-831), stacked NumPy math for the whole batch."""
+        w2i, src, ijk = geo.pose_arrays_batch(camera_projections, self.volumes)
+        if not self.volumes:
+            n = len(camera_projections)
+            src, ijk = np.zeros((n, 1, 3), dtype=np.float32), np.zeros((n, 1, 12), dtype=np.float32)
         return w2i, src, ijk
+
+    def _next_noise_seed(self) -> int:
+        seed = (self.noise_seed if self.noise_seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFF) + self._noise_calls
+        self._noise_calls += 1
+        return seed & 0xFFFFFFFFFFFFFFFF
 
     def _project_batch(self, camera_projections, want="intensity", out=None, raw=False):
         sizes = {tuple(p.intrinsic.sensor_size) for p in camera_projections}
@@ -399,8 +415,25 @@ class Projector(object):
             raise ValueError("all camera projections of one call must share the sensor size")
         W, H = sizes.pop()
         w2i, src, ijk = self._pose_arrays(camera_projections)
-        source_world = np.stack([np.asarray(p.center_in_world, dtype=np.float64).reshape(-1)[:3] for p in camera_projections]).astype(np.float32)
+        source_world = None
+        if self.meshes:
+            source_world = np.stack([np.asarray(p.center_in_world, dtype=np.float64).reshape(-1)[:3] for p in camera_projections]).astype(np.float32)
+        if self.collected_energy and want == "intensity" and not raw:
+            # the scale uses each view's own focal lengths (reference :839-840); views that differ are projected one by one
+            fs = [(p.intrinsic.fx, p.intrinsic.fy) for p in camera_projections]
+            if any(f != fs[0] for f in fs):
+                if out is None:
+                    out = self._new_images((len(camera_projections), H, W))
+                for i, p in enumerate(camera_projections):
+                    self._run(w2i[i:i + 1], src[i:i + 1], ijk[i:i + 1], W, H, want, out[i:i + 1], raw, p.intrinsic,
+                              None if source_world is None else source_world[i:i + 1])
+                return out
         return self._run(w2i, src, ijk, W, H, want, out, raw, camera_projections[0].intrinsic, source_world)
+
+    def _new_images(self, shape) -> np.ndarray:
+        """Result array: page-locked when the pool has room (see ``pinned_output``), else a plain ndarray."""
+        arr = self._pool.take(shape) if self._pool is not None else None
+        return arr if arr is not None else np.empty(shape, dtype=np.float32)
 
     def _run(self, w2i, src, ijk, W, H, want, out, raw, intrinsic, source_world=None):
         lib, h = _lib.load(), self._h
@@ -416,13 +449,16 @@ class Projector(object):
             self._upload_meshes()
             wfm = np.stack([np.asarray(m.world_from_ijk.toarray(), dtype=np.float32).reshape(12) for m in self.meshes])
             if n > chunk:
-                if want == "intensity+photon_prob" or out is not None:
-                    raise ValueError("batched mesh projection: pass at most %d views per call here" % chunk)
-                parts = [self._run(w2i[a:a + chunk], src[a:a + chunk], ijk[a:a + chunk], W, H, want, None, raw, intrinsic, source_world[a:a + chunk])
-                         for a in range(0, n, chunk)]
-                if want == "intensity" and self.neglog and not raw and len(parts) > 1:
-                    pass  # neglog is per image; only the "any constant image zeroes the batch" quirk is per call
-                return np.concatenate(parts, axis=0)
+                rng = range(0, n, chunk)
+                if want == "intensity+photon_prob":
+                    parts = [self._run(w2i[a:a + chunk], src[a:a + chunk], ijk[a:a + chunk], W, H, want, None, raw, intrinsic, source_world[a:a + chunk])
+                             for a in rng]
+                    return np.concatenate([p[0] for p in parts], axis=0), np.concatenate([p[1] for p in parts], axis=0)
+                if out is None:
+                    out = self._new_images((n, H, W)) if want == "intensity" else np.empty((n, len(self.all_materials), H, W), dtype=np.float32)
+                for a in rng:  # neglog is per image, so chunks give what one batch would
+                    self._run(w2i[a:a + chunk], src[a:a + chunk], ijk[a:a + chunk], W, H, want, out[a:a + chunk], raw, intrinsic, source_world[a:a + chunk])
+                return out
             wfm_all = np.ascontiguousarray(np.broadcast_to(wfm[None], (n,) + wfm.shape), dtype=np.float32)
             sw = np.ascontiguousarray(source_world, dtype=np.float32).reshape(n, 3)
             _lib.check(lib.drr_set_mesh_poses(h, n, _lib.ptr(wfm_all), _lib.ptr(sw), float(self.source_to_detector_distance * 2)), h)
@@ -448,8 +484,7 @@ class Projector(object):
             if k is None:
                 raise ValueError("collected_energy needs camera intrinsics (use project(), not project_arrays())")
             pixel_area = (self.source_to_detector_distance / k.fx) * (self.source_to_detector_distance / k.fy)
-        seed = (self.noise_seed if self.noise_seed is not None else int(np.random.SeedSequence().entropy) & 0xFFFFFFFFFFFF) + self._noise_calls
-        self._noise_calls += 1
+        seed = self._next_noise_seed() if (flags & _lib.POST_NOISE) else 0
         M = len(self.all_materials)
         if want == "intensity+photon_prob":  # raw kernel outputs (project_kernel.cu:644-645), no post-processing
             images = np.empty((n, H, W), dtype=np.float32)
@@ -458,11 +493,13 @@ class Projector(object):
                                        0, _lib.ptr(images), _lib.ptr(pprob), None, _lib.MEM_HOST), h)
             return images, pprob
         if want == "intensity":
-            images = out if out is not None else np.empty((n, H, W), dtype=np.float32)
+            images = out if out is not None else self._new_images((n, H, W))
+            if isinstance(images, np.ndarray) and (images.dtype != np.float32 or not images.flags.c_contiguous or images.size != n * H * W):
+                raise ValueError(f"out must be a C-contiguous float32 array of shape ({n}, {H}, {W})")
             mem = _lib.MEM_DEVICE if hasattr(images, "data_ptr") and images.is_cuda else _lib.MEM_HOST
             _lib.check(lib.drr_project(h, n, W, H, _lib.ptr(w2i), _lib.ptr(src), _lib.ptr(ijk), float(self.max_ray_length), flags,
                                        float(self.photon_count), float(self.intensity_upper_bound or 0.0), float(pixel_area),
-                                       seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(images), None, None, mem), h)
+                                       seed, _lib.ptr(images), None, None, mem), h)
             return images
         area = out if out is not None else np.empty((n, M, H, W), dtype=np.float32)
         mem = _lib.MEM_DEVICE if hasattr(area, "data_ptr") and area.is_cuda else _lib.MEM_HOST
@@ -571,6 +608,12 @@ class Projector(object):
     def last_sample_count(self) -> int:
         s = ctypes.c_ulonglong(0)
         _lib.check(_lib.load().drr_last_sample_count(self._h, ctypes.byref(s)), self._h)
+        return int(s.value)
+
+    def last_window_samples(self) -> int:
+        """Of ``last_sample_count``, the steps inside the volume's window (single-volume lock-step kernel only)."""
+        s = ctypes.c_ulonglong(0)
+        _lib.check(_lib.load().drr_last_window_samples(self._h, ctypes.byref(s)), self._h)
         return int(s.value)
 
     def launch_count(self) -> int:

@@ -187,6 +187,13 @@ int drr_postprocess(drr_ctx* ctx, float* images, const float* photon_prob, int n
 int drr_last_timing(const drr_ctx* ctx, float* ms3);
 /* Sum over the last batch of max(num_steps, 0) (x volumes traced) -- SURVEY.md 8(d) "S_view". */
 int drr_last_sample_count(const drr_ctx* ctx, unsigned long long* samples);
+/* Of those, the steps that fell inside a volume's [lo, hi] window (the samples that fetch density); filled by the
+ * single-volume lock-step kernel, 0 otherwise.  bench.py's gather rate is quoted on this figure. */
+int drr_last_window_samples(const drr_ctx* ctx, unsigned long long* samples);
+/* Page-locked host memory for image outputs, so that the device-to-host copy at the end of drr_project runs at full PCIe
+ * rate.  Replaces: the pageable ndarray cupy's `.get()` returns at projector.py:786-787. */
+int drr_host_alloc(size_t bytes, void** out);
+int drr_host_free(void* p);
 /* Number of kernels this library launched since the handle was created. */
 int drr_launch_count(const drr_ctx* ctx, unsigned long long* launches);
 /* Block until all work of the handle has finished. */

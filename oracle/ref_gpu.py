@@ -134,6 +134,12 @@ class RefProjector:
             pass
 
 
+def shutdown():
+    """Wait for the device to go idle (every RefProjector should have been closed)."""
+    if _lib is not None:
+        _lib.ref_shutdown()
+
+
 def ref_tide(ts_peel: np.ndarray, far_limit: float):
     """The reference's kernelTide on ``ts_peel`` [n_rays, 32] (peel layout); returns (ts, facing) cleaned."""
     ts = np.ascontiguousarray(ts_peel, dtype=np.float32).copy()

@@ -308,4 +308,10 @@ int ref_destroy(void* hp) {
     return 0;
 }
 
+// End of a run: nothing of the harness may still be executing when the process exits.
+int ref_shutdown() {
+    cudaDeviceSynchronize();
+    return 0;
+}
+
 }  // extern "C"
