@@ -811,6 +811,53 @@ static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, co
     return spread > 4.0f ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
 }
 
+// Slack of the lock-step kernels' staged boxes and window tests for this batch (see drr_march_warp.cu).  A segment of S steps is
+// bounded from alpha and fma(S, step, alpha); the alpha the kernel really reaches after j <= S sequential fp32 additions can be
+// (S / 2 + 1) ulps of the largest alpha away from that, i.e. that many ulps times |row of ijk_from_world| voxels, plus the
+// roundings of the coordinate FMAs themselves.  C2 (alpha <= 1100 mm, 0.8 mm voxels) needs 0.003 voxel; a 0.1 mm K-wire grid seen
+// from a metre away 0.05.  Returns false when a volume would need more than a quarter voxel: such scenes take the per-ray kernels.
+static bool march_slack(const drr_ctx* c, int n_views, const float* src_ijk, const float* ijk_from_world, float max_ray_length,
+                        MarchParams& P) {
+    const int V = (int)c->vols.size();
+    const double S = 64.0;  // the longest segment of drr_march_warp.cu (SEG_TEX)
+    double worst_vox = 0.0, worst_a = 0.0;
+    for (int i = 0; i < n_views; i++)
+        for (int v = 0; v < V; v++) {
+            const float* A = ijk_from_world + ((size_t)i * V + v) * 12;
+            const float* sp = src_ijk + ((size_t)i * V + v) * 3;
+            const VolHost& h = c->vols[v];
+            const float a9[9] = {A[0], A[1], A[2], A[4], A[5], A[6], A[8], A[9], A[10]};
+            float inv[9];
+            invert3(a9, inv);
+            double alpha_max = 0.0;
+            const double hi[3] = {h.ni - 0.5, h.nj - 0.5, h.nk - 0.5};
+            for (int k = 0; k < 8; k++) {
+                const double d[3] = {((k & 1) ? hi[0] : -0.5) - sp[0], ((k & 2) ? hi[1] : -0.5) - sp[1], ((k & 4) ? hi[2] : -0.5) - sp[2]};
+                double w2 = 0.0;
+                for (int r = 0; r < 3; r++) {
+                    const double w = inv[3 * r] * d[0] + inv[3 * r + 1] * d[1] + inv[3 * r + 2] * d[2];
+                    w2 += w * w;
+                }
+                alpha_max = fmax(alpha_max, sqrt(w2));
+            }
+            if (!(alpha_max > 0.0) || !std::isfinite(alpha_max)) alpha_max = 1.0e9;  // singular pose matrix: no bound
+            if (max_ray_length > 0.0f) alpha_max = fmin(alpha_max, (double)max_ray_length);
+            alpha_max = fmax(alpha_max, 2.0);  // rays start at alpha ~ 1 (ray_length)
+            const double ulp_a = ldexp(1.0, (int)floor(log2(alpha_max)) - 23);
+            double row = 0.0;
+            for (int r = 0; r < 3; r++) row = fmax(row, sqrt((double)a9[3 * r] * a9[3 * r] + (double)a9[3 * r + 1] * a9[3 * r + 1] + (double)a9[3 * r + 2] * a9[3 * r + 2]));
+            const double nmax = fmax(fmax(h.ni, h.nj), h.nk) + 2.0;
+            const double ulp_p = ldexp(1.0, (int)floor(log2(nmax)) - 23);
+            worst_vox = fmax(worst_vox, (S / 2 + 1) * ulp_a * row + 4.0 * ulp_p);
+            worst_a = fmax(worst_a, (S / 2 + 1) * ulp_a);
+        }
+    const double lo = fmax(0.01, 0.002 + 1.25 * worst_vox);
+    P.slack_lo = (float)lo;
+    P.slack_hi = (float)(lo + 0.0025);          // + the 1 / 512 round-up of the fixed-point coordinate
+    P.slack_alpha = (float)fmax(0.01, 1.5 * worst_a);
+    return lo <= 0.25 && P.slack_alpha <= 0.25f * c->step + 0.01f;
+}
+
 static int ensure(drr_ctx* c, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes && *p) return DRR_OK;
     cudaFree(*p);
@@ -923,12 +970,13 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         if (sampler < 0) return fail(c, DRR_E_STATE, "drr_project: volume 0 has neither cell records nor a texture");
         P.tex_eighths = sampler == DRR_SAMPLER_ALU ? 0 : (sampler == DRR_SAMPLER_TEX ? 8 : c->tex_eighths);
     }
+    const bool lockstep_ok = V > 0 && march_slack(c, n_views, src_ijk, ijk_from_world, max_ray_length, P);
     CU(c, cudaEventRecord(c->ev[1], s));
     if (V == 0) {
         if (meshes) { CU(c, drr_launch_march_meshonly(P, s)); c->launches += 1; }
         else CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
     } else if (single) {
-        if (h_has_cells(c) && pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0) {
+        if (h_has_cells(c) && (c->variant == 0 ? lockstep_ok : true) && pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0) {
             CU(c, drr_launch_march_warp(P, c->n_sm, s));  // persistent: every warp pulls 8x4-pixel tiles from the queue
         } else {
             int occ = drr_march_single_occupancy(M);
@@ -941,7 +989,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         for (int v = 0; v < V; v++)
             if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_project: volume %d has no raw arrays", v);
         // Tiles whose rays see a single volume take the lock-step kernel; the others are listed for the general one.
-        bool split = !c->attenuate_outside && c->variant == 0;  // (V == 1 gets here only with meshes)
+        bool split = !c->attenuate_outside && c->variant == 0 && lockstep_ok;  // (V == 1 gets here only with meshes)
         int sampler = c->sampler;
         for (int v = 0; v < V; v++)  // a volume without coefficient records: texture unit only; without a texture: FMA pipes only
             if (!c->vols[v].cellc && c->vols[v].tex) sampler = DRR_SAMPLER_TEX;

@@ -45,7 +45,21 @@
 #ifndef WARPS_PER_BLOCK
 #define WARPS_PER_BLOCK 8
 #endif
+#ifndef SWB
+#define SWB 5                          // single-volume kernel: warps per block ...
+#endif
+#ifndef SMB
+#define SMB 4                          // ... and resident blocks per SM it is compiled for (register budget 65536 / (32 SWB SMB))
+#endif
 #define MULTI_MAXV 4                   // volumes the multi-volume variant handles
+#ifndef RAYS_PER_LANE
+#define RAYS_PER_LANE 2                // single-volume kernel: a warp walks an 8 x (4 * RAYS_PER_LANE) pixel tile
+#endif
+// Slack of the staged box (MarchParams::slack_lo / slack_hi, voxels) and of the window tests (slack_alpha, mm): they cover the
+// drift of the accumulated fp32 alpha against alpha + S * step (<= S / 2 ulps of alpha; times |d| in voxels) and, on the high
+// side, the 1 / 512 by which a fixed-point coordinate rounds up.  The host derives them per launch from the scene's largest
+// alpha and finest voxel pitch (drr_capi.cu: march_slack) -- 0.01 / 0.0125 voxel and 0.01 mm for C2 -- and routes scenes that
+// would need more than a quarter voxel to the per-ray kernels.
 
 // tile id -> view and this lane's pixel (8x4 tiles, row-major per view)
 __device__ __forceinline__ void tile_pixel(const MarchParams& P, unsigned tile, int lane, int& view, int& udx, int& vdx) {
@@ -140,73 +154,116 @@ __device__ __forceinline__ void w_slow_sample(const VolDev& vol, float x, float 
 
 // KTEX = how many samples of every group of 8 consecutive steps are fetched by the texture unit; the others are
 // interpolated on the FMA pipes from the staged cell records.  8 = TEX only (no records staged), 0 = ALU only.
+// R = rays per lane: a warp walks R * 32 rays (an 8 x 4R pixel tile) through the same staged boxes, so the per-segment
+// work (bounding, staging, classification) is shared by R * 32 * S samples; the sample loops run once per ray.
 // MULTI: the scene has more volumes; [olo, ohi] is the hull of this ray's windows in the OTHER volumes.  Segments that
 // come near it are marched step by step with the reference's priority pick over all volumes (K.cu:458-547); the
 // caller has established that the shared label cache never serves foreign labels on this tile (see march_multi_kernel).
-template <int NM, int KTEX, bool MULTI>
-__device__ __forceinline__ void march_core(const VolDev& vol, const float step, const float sx, const float sy, const float sz, const float dx,
-                                           const float dy, const float dz, const float lo, const float hi, float alpha, const int num_steps,
-                                           float4* s_coef, uint8_t* s_code, int lane, float* acc, const MarchParams* MP = nullptr,
-                                           unsigned tile = 0, float olo = 1.0f, float ohi = -1.0f) {
+template <int NM, int KTEX, bool MULTI, int R>
+__device__ __forceinline__ void march_core(const VolDev& vol, const float step, const float sx, const float sy, const float sz,
+                                           const float (&dx)[R], const float (&dy)[R], const float (&dz)[R], const float (&lo)[R],
+                                           const float (&hi)[R], float (&alpha)[R], const int (&num_steps)[R], float4* s_coef, uint8_t* s_code,
+                                           int lane, float (&acc)[R][NM], const float slack_lo, const float slack_hi, const float slack_a,
+                                           const MarchParams* MP = nullptr, unsigned tile = 0, float olo = 1.0f, float ohi = -1.0f) {
+    static_assert(!MULTI || R == 1, "the multi-volume march walks one ray per lane");
     constexpr bool USE_TEX = KTEX > 0;      // general / slow samples go through the texture unit when there is one
     constexpr bool STAGE_COEF = KTEX < 8;
+    int ns_max = 0;
 #pragma unroll
-    for (int m = 0; m < NM; m++) acc[m] = 0.0f;
-    const int last = num_steps - 1;
-    const int t_end = __reduce_max_sync(0xffffffffu, num_steps);
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int m = 0; m < NM; m++) acc[r][m] = 0.0f;
+        ns_max = max(ns_max, num_steps[r]);
+    }
+    const int t_end = __reduce_max_sync(0xffffffffu, ns_max);
     if (t_end == 0) return;
 
     // ---- before the volume: replay the fp32 alpha accumulation only (K.cu:552) ----
-    // Lower bound of the first in-range step of each lane; `drift` bounds how far the accumulated
+    // Lower bound of the first in-range step of each ray; `drift` bounds how far the accumulated
     // alpha can be from minAlpha + t*step.
     int t = 0;
     {
         int n0 = 0x7fffffff;
-        if (num_steps > 0) {
-            float drift = (float)num_steps * 0x1p-24f * fmaxf(MULTI ? fmaxf(hi, ohi) : hi, 1.0f);
-            n0 = max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(lo, alpha), drift), step), 2.0e9f)) - 2);
-            n0 = min(n0, num_steps);
-            if (MULTI) {
-                if (lo > hi) n0 = num_steps;  // this ray never enters the volume
-                if (olo <= ohi) n0 = min(n0, max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(olo, alpha), drift), step), 2.0e9f)) - 2));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (num_steps[r] > 0) {
+                float drift = (float)num_steps[r] * 0x1p-24f * fmaxf(MULTI ? fmaxf(hi[r], ohi) : hi[r], 1.0f);
+                int n = max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(lo[r], alpha[r]), drift), step), 2.0e9f)) - 2);
+                n = min(n, num_steps[r]);
+                if (MULTI) {
+                    if (lo[r] > hi[r]) n = num_steps[r];  // this ray never enters the volume
+                    if (olo <= ohi) n = min(n, max(0, (int)floorf(fminf(__fdiv_rn(__fsub_rn(__fsub_rn(olo, alpha[r]), drift), step), 2.0e9f)) - 2));
+                }
+                n0 = min(n0, n);
             }
         }
         const int n_skip = __reduce_min_sync(0xffffffffu, n0);
-        if (num_steps > 0) {  // (lanes without a ray have nothing to keep in step)
-            if (alpha >= 0x1p-100f) alpha = alpha_jump(alpha, step, n_skip);  // == n_skip times alpha += step
-            else for (int i = 0; i < n_skip; i++) alpha = __fadd_rn(alpha, step);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (num_steps[r] > 0) {  // (rays that do not exist have nothing to keep in step)
+                if (alpha[r] >= 0x1p-100f) alpha[r] = alpha_jump(alpha[r], step, n_skip);  // == n_skip times alpha += step
+                else for (int i = 0; i < n_skip; i++) alpha[r] = __fadd_rn(alpha[r], step);
+            }
         }
         t = n_skip;
     }
 
-    float cur = 0.0f;
-    int live = -1;
+    float cur[R];
+    int live[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { cur[r] = 0.0f; live[r] = -1; }
     const int nxm = vol.ni - 2, nym = vol.nj - 2, nzm = vol.nk - 2;  // max cell base
     const float sxm = sx - 1.0f, sym = sy - 1.0f, szm = sz - 1.0f;
+    // The sample loops below exist ONCE in the code and always work on ray 0 of the lane; after each pass the rays of the lane
+    // are rotated by one place, so R passes serve every ray and leave the order as it was.  (Unrolling the passes instead doubles
+    // the code of the active path past the 32 KB instruction cache: 2.4 "no instruction" stall cycles per issue, 30 % slower.)
+    float rdx[R], rdy[R], rdz[R], rlo[R], rhi[R];
+    int rns[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { rdx[r] = dx[r]; rdy[r] = dy[r]; rdz[r] = dz[r]; rlo[r] = lo[r]; rhi[r] = hi[r]; rns[r] = num_steps[r]; }
+    auto rotate = [&]() {
+        if (R > 1) {
+            auto rot = [&](auto& x) {
+                auto x0 = x[0];
+#pragma unroll
+                for (int r = 0; r + 1 < R; r++) x[r] = x[r + 1];
+                x[R - 1] = x0;
+            };
+            rot(rdx); rot(rdy); rot(rdz); rot(rlo); rot(rhi); rot(rns); rot(alpha); rot(cur); rot(live);
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const float a0 = acc[0][m];
+#pragma unroll
+                for (int r = 0; r + 1 < R; r++) acc[r][m] = acc[r + 1][m];
+                acc[R - 1][m] = a0;
+            }
+        }
+    };
 
     while (t < t_end) {
         // the march goes on to the far end of the farthest volume (K.cu:321-334); past this volume's window nothing is added
         if (MULTI) {
-            if (__all_sync(0xffffffffu, t >= num_steps || (alpha > hi + 0.01f && (olo > ohi || alpha > ohi + 0.01f)))) break;
+            if (__all_sync(0xffffffffu, t >= rns[0] || (alpha[0] > rhi[0] + slack_a && (olo > ohi || alpha[0] > ohi + slack_a)))) break;
             const int S0 = min(STAGE_COEF ? SEG_ALU : SEG_TEX, t_end - t);
-            const float a1 = __fmaf_rn((float)S0, step, alpha);
-            const bool near_other = (t < num_steps) && (olo <= ohi) && !(a1 < olo - 0.01f) && !(alpha > ohi + 0.01f);
+            const float a1 = __fmaf_rn((float)S0, step, alpha[0]);
+            const bool near_other = (t < rns[0]) && (olo <= ohi) && !(a1 < olo - slack_a) && !(alpha[0] > ohi + slack_a);
             if (__any_sync(0xffffffffu, near_other)) {
                 // ---- mixed segment: priority pick over every volume, sample by sample ----------------
-                w_checkin<NM>(cur, live, acc);
+                w_checkin<NM>(cur[0], live[0], acc[0]);
                 const MarchParams& P = *MP;
                 const int V = P.V;
+                const int last = rns[0] - 1;
                 int view, udx, vdx;  // recomputed from the tile id rather than kept in registers through the march
                 tile_pixel(P, tile, lane, view, udx, vdx);
                 udx = min(udx, P.W - 1); vdx = min(vdx, P.H - 1);
                 const ViewDev* mvw = P.views + view;
-                const Ray r = make_ray(mvw->w2i, udx, vdx);
+                const Ray ry = make_ray(mvw->w2i, udx, vdx);
                 float dxs[MULTI_MAXV], dys[MULTI_MAXV], dzs[MULTI_MAXV], los[MULTI_MAXV], his[MULTI_MAXV];
 #pragma unroll
                 for (int i = 0; i < MULTI_MAXV; i++) {
                     dxs[i] = dys[i] = dzs[i] = 0.0f; los[i] = 1.0f; his[i] = -1.0f;  // empty window: never picked
                     if (i >= V || P.enabled[i] == 0) continue;
-                    ray_dir_ijk(r, mvw->ijk[i], dxs[i], dys[i], dzs[i]);
+                    ray_dir_ijk(ry, mvw->ijk[i], dxs[i], dys[i], dzs[i]);
                     float lo_i, hi_i;
                     if (slab_test(dxs[i], dys[i], dzs[i], mvw->src[i][0], mvw->src[i][1], mvw->src[i][2], P.vol[i].ni, P.vol[i].nj, P.vol[i].nk,
                                   P.max_ray_length, lo_i, hi_i)) { los[i] = lo_i; his[i] = hi_i; }
@@ -217,6 +274,7 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                 int hidx[4] = {0, 0, 0, 0}, hdep[4] = {0, 0, 0, 0};
                 const size_t npix = (size_t)P.W * P.H;
                 const size_t hbase = (((size_t)view * P.mesh_layers) * npix + (size_t)vdx * P.W + udx) * P.max_hits;
+                float al = alpha[0];
                 for (int s = 0; s < S0; s++, t++) {
                     bool inside_mesh = false;
                     if (carve) {
@@ -225,15 +283,15 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                             if (j >= P.mesh_layers || P.layer_valid[j] == 0) continue;
                             const float* ha = P.hit_alphas + hbase + (size_t)j * npix * P.max_hits;
                             const int8_t* hf = P.hit_facing + hbase + (size_t)j * npix * P.max_hits;
-                            while (hidx[j] < P.max_hits && hf[hidx[j]] != 0 && ha[hidx[j]] < alpha) { hdep[j] += hf[hidx[j]]; hidx[j] += 1; }
+                            while (hidx[j] < P.max_hits && hf[hidx[j]] != 0 && ha[hidx[j]] < al) { hdep[j] += hf[hidx[j]]; hidx[j] += 1; }
                             if (hdep[j] > 0) inside_mesh = true;
                         }
                     }
-                    if (t < num_steps && !inside_mesh) {
+                    if (t < rns[0] && !inside_mesh) {
                         int curr_priority = 0x7fffffff, n_at = 0;  // K.cu:458-496; priorities are distinct here (drr_capi.cu)
 #pragma unroll
                         for (int i = 0; i < MULTI_MAXV; i++) {
-                            if (alpha < los[i] || alpha > his[i]) continue;
+                            if (al < los[i] || al > his[i]) continue;
                             if (P.priority[i] < curr_priority) { curr_priority = P.priority[i]; n_at = 1; }
                             else if (P.priority[i] == curr_priority) n_at += 1;
                         }
@@ -241,15 +299,16 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                             const float weight = __fmul_rn(__fdiv_rn(1.0f, (float)n_at), (t == 0 || t == last) ? 0.5f : 1.0f);  // K.cu:530-537
 #pragma unroll
                             for (int i = 0; i < MULTI_MAXV; i++) {
-                                if (alpha < los[i] || alpha > his[i] || P.priority[i] != curr_priority) continue;
-                                const float x = __fmaf_rn(alpha, dxs[i], mvw->src[i][0]), y = __fmaf_rn(alpha, dys[i], mvw->src[i][1]),
-                                            z = __fmaf_rn(alpha, dzs[i], mvw->src[i][2]);
-                                w_slow_sample_call<NM, USE_TEX>(P.vol[i], x, y, z, weight, acc);
+                                if (al < los[i] || al > his[i] || P.priority[i] != curr_priority) continue;
+                                const float x = __fmaf_rn(al, dxs[i], mvw->src[i][0]), y = __fmaf_rn(al, dys[i], mvw->src[i][1]),
+                                            z = __fmaf_rn(al, dzs[i], mvw->src[i][2]);
+                                w_slow_sample_call<NM, USE_TEX>(P.vol[i], x, y, z, weight, acc[0]);
                             }
                         }
                     }
-                    alpha = __fadd_rn(alpha, step);  // K.cu:552
+                    al = __fadd_rn(al, step);  // K.cu:552
                 }
+                alpha[0] = al;
                 continue;
             }
         }
@@ -265,27 +324,37 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             return bx * by * bz <= cap && max(bx, max(by, bz)) <= 255 && (bx * by <= 255 || bz == 1);
         };
         for (;;) {
-            float a1 = __fmaf_rn((float)S, step, alpha);
-            bool part = (t < num_steps) && !(a1 < lo - 0.01f) && !(alpha > hi + 0.01f);
-            float p0x = __fmaf_rn(alpha, dx, sxm), p1x = __fmaf_rn(a1, dx, sxm);  // p = x - 1 to within an ulp: a bound, the slack covers it
-            float p0y = __fmaf_rn(alpha, dy, sym), p1y = __fmaf_rn(a1, dy, sym);
-            float p0z = __fmaf_rn(alpha, dz, szm), p1z = __fmaf_rn(a1, dz, szm);
-            // slack: the drift of the accumulated alpha against a1 (both sides) and, on the high side, the 1/512 by which a
-            // sample's fixed-point coordinate can round up into the next cell
-            int lx = max(-2, min(nxm, (int)floorf(fminf(p0x, p1x) - 0.01f))), hx = max(-2, min(nxm, (int)floorf(fmaxf(p0x, p1x) + 0.0125f)));
-            int ly = max(-2, min(nym, (int)floorf(fminf(p0y, p1y) - 0.01f))), hy = max(-2, min(nym, (int)floorf(fmaxf(p0y, p1y) + 0.0125f)));
-            int lz = max(-2, min(nzm, (int)floorf(fminf(p0z, p1z) - 0.01f))), hz = max(-2, min(nzm, (int)floorf(fmaxf(p0z, p1z) + 0.0125f)));
-            if (!part) { lx = ly = lz = 0x7fffffff; hx = hy = hz = (int)0x80000000; }
+            int lx = 0x7fffffff, ly = 0x7fffffff, lz = 0x7fffffff, hx = (int)0x80000000, hy = (int)0x80000000, hz = (int)0x80000000;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float a1 = __fmaf_rn((float)S, step, alpha[r]);
+                const bool part = (t < rns[r]) && !(a1 < rlo[r] - slack_a) && !(alpha[r] > rhi[r] + slack_a);
+                const float p0x = __fmaf_rn(alpha[r], rdx[r], sxm), p1x = __fmaf_rn(a1, rdx[r], sxm);  // p = x - 1 to within an ulp: a bound, the slack covers it
+                const float p0y = __fmaf_rn(alpha[r], rdy[r], sym), p1y = __fmaf_rn(a1, rdy[r], sym);
+                const float p0z = __fmaf_rn(alpha[r], rdz[r], szm), p1z = __fmaf_rn(a1, rdz[r], szm);
+                if (part) {
+                    // slack: the drift of the accumulated alpha against a1 (both sides) and, on the high side, the 1/512 by which a
+                    // sample's fixed-point coordinate can round up into the next cell (slack_lo / slack_hi: drr_capi.cu, march_slack)
+                    lx = min(lx, (int)floorf(fminf(p0x, p1x) - slack_lo)); hx = max(hx, (int)floorf(fmaxf(p0x, p1x) + slack_hi));
+                    ly = min(ly, (int)floorf(fminf(p0y, p1y) - slack_lo)); hy = max(hy, (int)floorf(fmaxf(p0y, p1y) + slack_hi));
+                    lz = min(lz, (int)floorf(fminf(p0z, p1z) - slack_lo)); hz = max(hz, (int)floorf(fmaxf(p0z, p1z) + slack_hi));
+                }
+            }
+            // clamping commutes with the warp-wide min / max: do it once, on the reduced values
             blx = __reduce_min_sync(0xffffffffu, lx); bly = __reduce_min_sync(0xffffffffu, ly); blz = __reduce_min_sync(0xffffffffu, lz);
             int bhx = __reduce_max_sync(0xffffffffu, hx), bhy = __reduce_max_sync(0xffffffffu, hy), bhz = __reduce_max_sync(0xffffffffu, hz);
             any = bhx >= blx;
             if (!any) break;
+            blx = max(-2, min(nxm, blx)); bly = max(-2, min(nym, bly)); blz = max(-2, min(nzm, blz));
+            bhx = max(-2, min(nxm, bhx)); bhy = max(-2, min(nym, bhy)); bhz = max(-2, min(nzm, bhz));
             nx = bhx - blx + 1; ny = bhy - bly + 1; nz = bhz - blz + 1;
             if (box_fits(nx, ny, nz) || S == 1) break;
             S >>= 1;
         }
         if (!any) {  // nobody samples in this segment: just advance alpha
-            for (int s = 0; s < S; s++) alpha = __fadd_rn(alpha, step);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                for (int s = 0; s < S; s++) alpha[r] = __fadd_rn(alpha[r], step);
             t += S;
             continue;
         }
@@ -294,15 +363,22 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             // Even a single step of this tile does not fit the staging buffer (rays far apart compared with
             // the voxel size): take the generic per-sample path for this step.  Correct for any geometry;
             // the host picks the per-ray kernel for such set-ups (drr_capi.cu: pick_variant).
-            w_checkin<NM>(cur, live, acc);
-            for (int s = 0; s < S; s++, t++) {
-                const bool inr = (t < num_steps) && !(alpha < lo) && !(alpha > hi);
-                if (inr) {
-                    const float x = __fmaf_rn(alpha, dx, sx), y = __fmaf_rn(alpha, dy, sy), z = __fmaf_rn(alpha, dz, sz);
-                    w_slow_sample_call<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc);
+#pragma unroll 1
+            for (int pass = 0; pass < R; pass++) {
+                w_checkin<NM>(cur[0], live[0], acc[0]);
+                const int last = rns[0] - 1;
+                int tt = t;
+                for (int s = 0; s < S; s++, tt++) {
+                    const bool inr = (tt < rns[0]) && !(alpha[0] < rlo[0]) && !(alpha[0] > rhi[0]);
+                    if (inr) {
+                        const float x = __fmaf_rn(alpha[0], rdx[0], sx), y = __fmaf_rn(alpha[0], rdy[0], sy), z = __fmaf_rn(alpha[0], rdz[0], sz);
+                        w_slow_sample_call<NM, USE_TEX>(vol, x, y, z, (tt == 0 || tt == last) ? 0.5f : 1.0f, acc[0]);
+                    }
+                    alpha[0] = __fadd_rn(alpha[0], step);
                 }
-                alpha = __fadd_rn(alpha, step);
+                rotate();
             }
+            t += S;
             continue;
         }
 
@@ -368,9 +444,11 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         const int code0 = __shfl_sync(0xffffffffu, first_code, 0);
         if (first_code < 0) first_code = code0;
         const bool seg_uniform = __all_sync(0xffffffffu, same && first_code == code0) && code0 != 0xFF;
-        // every lane inside its [lo, hi] window and away from its half-weighted end samples for the whole segment?
-        const bool lane_allin = (t > 0) && (t + S < num_steps) && !(alpha < lo) &&
-                                !(__fmaf_rn((float)S, step, alpha) + 0.01f > hi);
+        // every ray inside its [lo, hi] window and away from its half-weighted end samples for the whole segment?
+        bool lane_allin = t > 0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            lane_allin = lane_allin && (t + S < rns[r]) && !(alpha[r] < rlo[r]) && !(__fmaf_rn((float)S, step, alpha[r]) + slack_a > rhi[r]);
         const bool seg_allin = __all_sync(0xffffffffu, lane_allin);
 
         const float b1x = (float)(blx + 1), b1y = (float)(bly + 1), b1z = (float)(blz + 1);
@@ -378,184 +456,212 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
         const float kfx = __fmaf_rn(-256.0f, b1x, 8388608.0f), kfy = __fmaf_rn(-256.0f, b1y, 8388608.0f), kfz = __fmaf_rn(-256.0f, b1z, 8388608.0f);
         if (seg_uniform && seg_allin) {
             // ---- 3a. fast segment: one label, no range checks ------------------------------------
-            if (live != code0) {
-                w_checkin<NM>(cur, live, acc);
-                cur = w_checkout<NM>(code0, live, acc);
-            }
-            const int t_stop = t + S;
-            auto tex_sample = [&](float a) {
-                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                return tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
-            };
             // The unit's 1.8 fixed-point coordinate relative to the box, Q = floor(256 * (x - b1) + 0.5), in ONE FFMA per axis:
             // kq = 2^23 + 0.5 - 256 * b1 is exact (b1 >= 2 on interior cells, so kq < 2^23 where the grid is 0.5), the FMA
             // adds it to 256 * x without intermediate rounding, the sum is >= 2^23 (grid 1) and rounding DOWN leaves
             // 2^23 + Q in the mantissa: low byte = fraction, next byte = cell (box sides are < 256 cells).
             const float kqx = __fadd_rn(kfx, 0.5f), kqy = __fadd_rn(kfy, 0.5f), kqz = __fadd_rn(kfz, 0.5f);
-            auto alu_sample = [&](float a) {
-                const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kqx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kqy)),
-                               qz = __float_as_uint(__fmaf_rd(z, 256.0f, kqz));
-                const unsigned cells = __byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510);  // (cx, cy, cz, -)
-                const int idx = (int)__dp4a(cells, cell_w, 0u);
-                const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
-                return hw_trilinear_cell2q(qx, qy, qz, cA, cB);
-            };
-            if (KTEX == 8) {
+            const int t_stop = t + S;
+#pragma unroll 1
+            for (int pass = 0; pass < R; pass++) {
+                if (live[0] != code0) {
+                    w_checkin<NM>(cur[0], live[0], acc[0]);
+                    cur[0] = w_checkout<NM>(code0, live[0], acc[0]);
+                }
+                const float dxr = rdx[0], dyr = rdy[0], dzr = rdz[0];
+                float al = alpha[0], c = cur[0];
+                int tt = t;
+                // (Folding the - 0.5 into the FMA's addend would save three FADDs per fetch and is the same number except where the
+                // coordinate lies in [2^k, 2^k + 0.5) -- 0.5 % of the samples, half an ulp.  Measured: that moves enough fixed-point
+                // coordinates on rays that run along such a band to take C2's worst pixel from 4e-7 to 6.4e-6 of its line integral.)
+                auto tex_sample = [&](float a) {
+                    const float x = __fmaf_rn(a, dxr, sx), y = __fmaf_rn(a, dyr, sy), z = __fmaf_rn(a, dzr, sz);
+                    return tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
+                };
+                auto alu_sample = [&](float a) {
+                    const float x = __fmaf_rn(a, dxr, sx), y = __fmaf_rn(a, dyr, sy), z = __fmaf_rn(a, dzr, sz);
+                    const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kqx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kqy)),
+                                   qz = __float_as_uint(__fmaf_rd(z, 256.0f, kqz));
+                    const unsigned cells = __byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510);  // (cx, cy, cz, -)
+                    const int idx = (int)__dp4a(cells, cell_w, 0u);  // inside the staged box: the host sizes the slack for that (march_slack)
+                    const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
+                    return hw_trilinear_cell2q(qx, qy, qz, cA, cB);
+                };
+                if (KTEX == 8) {
 #pragma unroll 4
-                for (; t < t_stop; t++) {
-                    cur = __fadd_rn(cur, tex_sample(alpha));
-                    alpha = __fadd_rn(alpha, step);  // K.cu:552
-                }
-            } else if (KTEX == 0) {
+                    for (; tt < t_stop; tt++) {
+                        c = __fadd_rn(c, tex_sample(al));
+                        al = __fadd_rn(al, step);  // K.cu:552
+                    }
+                } else if (KTEX == 0) {
 #pragma unroll 2
-                for (; t < t_stop; t++) {
-                    cur = __fadd_rn(cur, alu_sample(alpha));
-                    alpha = __fadd_rn(alpha, step);
+                    for (; tt < t_stop; tt++) {
+                        c = __fadd_rn(c, alu_sample(al));
+                        al = __fadd_rn(al, step);
+                    }
+                } else {
+                    // groups of 8 steps: the texture fetches are issued first, the FMA-pipe samples are computed while
+                    // they are in flight, and the running total receives the eight values in step order (K.cu:544-546)
+                    for (; tt + 8 <= t_stop; tt += 8) {
+                        float a[8], v[8];
+                        a[0] = al;
+#pragma unroll
+                        for (int j = 1; j < 8; j++) a[j] = __fadd_rn(a[j - 1], step);
+                        // which steps of the group use the texture unit: spread evenly (Bresenham)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 != (j * KTEX) / 8) v[j] = tex_sample(a[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 == (j * KTEX) / 8) v[j] = alu_sample(a[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) c = __fadd_rn(c, v[j]);
+                        al = __fadd_rn(a[7], step);
+                    }
+                    for (; tt < t_stop; tt++) {
+                        c = __fadd_rn(c, tex_sample(al));
+                        al = __fadd_rn(al, step);
+                    }
                 }
-            } else {
-                // groups of 8 steps: the texture fetches are issued first, the FMA-pipe samples are computed while
-                // they are in flight, and the running total receives the eight values in step order (K.cu:544-546)
-                for (; t + 8 <= t_stop; t += 8) {
-                    float a[8], r[8];
-                    a[0] = alpha;
-#pragma unroll
-                    for (int j = 1; j < 8; j++) a[j] = __fadd_rn(a[j - 1], step);
-                    // which steps of the group use the texture unit: spread evenly (Bresenham)
-#pragma unroll
-                    for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 != (j * KTEX) / 8) r[j] = tex_sample(a[j]);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) if (((j + 1) * KTEX) / 8 == (j * KTEX) / 8) r[j] = alu_sample(a[j]);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) cur = __fadd_rn(cur, r[j]);
-                    alpha = __fadd_rn(a[7], step);
-                }
-                for (; t < t_stop; t++) {
-                    cur = __fadd_rn(cur, tex_sample(alpha));
-                    alpha = __fadd_rn(alpha, step);
-                }
+                alpha[0] = al; cur[0] = c;
+                rotate();
             }
+            t = t_stop;
             continue;
         }
 
         // ---- 3b. general segment: per-sample label code and range check ----------------------------
         // four steps at a time, so that the texture fetches of a group are in flight together
-        for (int s0 = 0; s0 < S; s0 += 4) {
-            const int nb = min(4, S - s0);
-            float aj[4], rj[4];
-            aj[0] = alpha;
+#pragma unroll 1
+        for (int pass = 0; pass < R; pass++) {
+            const float dxr = rdx[0], dyr = rdy[0], dzr = rdz[0], lor = rlo[0], hir = rhi[0];
+            const int nsr = rns[0], last = rns[0] - 1;
+            float al = alpha[0], c = cur[0];
+            int lv = live[0], tt = t;
+            for (int s0 = 0; s0 < S; s0 += 4) {
+                const int nb = min(4, S - s0);
+                float aj[4], rj[4];
+                aj[0] = al;
 #pragma unroll
-            for (int j = 1; j < 4; j++) aj[j] = __fadd_rn(aj[j - 1], step);  // K.cu:552
-            // per step: in range?  (K.cu:472) -- then the texture fetches of the group, all in flight together -- then the label
-            // code of every sample's cell.  Cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1))
-            // from one round-down FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte.
-            // Two copies of this front part: segments whose lanes are all inside their windows (most general segments are
-            // "box not uniform" ones) need neither the range tests nor the end-sample test.
-            bool inr[4];
-            unsigned codes = 0;  // one byte per step
-            bool plain = true;
-            auto front = [&](auto all_inside) {
-                constexpr bool AI = decltype(all_inside)::value;
+                for (int j = 1; j < 4; j++) aj[j] = __fadd_rn(aj[j - 1], step);  // K.cu:552
+                // per step: in range?  (K.cu:472) -- then the texture fetches of the group, all in flight together -- then the label
+                // code of every sample's cell.  Cell of p = x - 1 (K.cu:402-404, 416) inside the box: 2^23 + floor(256 * (x - b1))
+                // from one round-down FFMA per axis (kf = 2^23 - 256 * b1, exact), cell index in the second byte.
+                // Two copies of this front part: segments whose lanes are all inside their windows (most general segments are
+                // "box not uniform" ones) need neither the range tests nor the end-sample test.
+                bool inr[4];
+                unsigned codes = 0;  // one byte per step
+                bool plain = true;
+                auto front = [&](auto all_inside) {
+                    constexpr bool AI = decltype(all_inside)::value;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    inr[j] = AI ? true : (j < nb && (t + j < num_steps) && !(aj[j] < lo) && !(aj[j] > hi));
-                    const float a = aj[j];
-                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                    rj[j] = 0.0f;
-                    if (USE_TEX && inr[j]) rj[j] = tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
-                }
+                    for (int j = 0; j < 4; j++) {
+                        inr[j] = AI ? true : (j < nb && (tt + j < nsr) && !(aj[j] < lor) && !(aj[j] > hir));
+                        const float a = aj[j];
+                        const float x = __fmaf_rn(a, dxr, sx), y = __fmaf_rn(a, dyr, sy), z = __fmaf_rn(a, dzr, sz);
+                        rj[j] = 0.0f;
+                        if (USE_TEX && inr[j]) rj[j] = tex3D<float>(vol.tex, __fsub_rn(x, 0.5f), __fsub_rn(y, 0.5f), __fsub_rn(z, 0.5f));  // K.cu:542
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float a = aj[j];
-                    const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                    const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
-                                   qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
-                    int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
-                    idx = inr[j] ? min(idx, ncell - 1) : 0;
-                    int code = s_code[idx];
-                    if (!AI && ((t + j == 0) | (t + j == last))) code = 0xFF;  // half-weighted end samples take the generic path
-                    codes |= (unsigned)code << (8 * j);
-                    plain = plain && (!inr[j] || code == live);
-                }
-            };
-            if (seg_allin && nb == 4) front(std::true_type{}); else front(std::false_type{});
-            if (USE_TEX && __all_sync(0xffffffffu, plain)) {
-                // the whole warp stays on its materials for the group (lanes out of range fetched nothing: + 0)
+                    for (int j = 0; j < 4; j++) {
+                        const float a = aj[j];
+                        const float x = __fmaf_rn(a, dxr, sx), y = __fmaf_rn(a, dyr, sy), z = __fmaf_rn(a, dzr, sz);
+                        const unsigned qx = __float_as_uint(__fmaf_rd(x, 256.0f, kfx)), qy = __float_as_uint(__fmaf_rd(y, 256.0f, kfy)),
+                                       qz = __float_as_uint(__fmaf_rd(z, 256.0f, kfz));
+                        int idx = (int)__dp4a(__byte_perm(__byte_perm(qx, qy, 0x0051), qz, 0x0510), cell_w, 0u);
+                        idx = inr[j] ? min(idx, ncell - 1) : 0;
+                        int code = s_code[idx];
+                        if (!AI && ((tt + j == 0) | (tt + j == last))) code = 0xFF;  // half-weighted end samples take the generic path
+                        codes |= (unsigned)code << (8 * j);
+                        plain = plain && (!inr[j] || code == lv);
+                    }
+                };
+                if (seg_allin && nb == 4) front(std::true_type{}); else front(std::false_type{});
+                if (USE_TEX && __all_sync(0xffffffffu, plain)) {
+                    // the whole warp stays on its materials for the group (lanes out of range fetched nothing: + 0)
 #pragma unroll
-                for (int j = 0; j < 4; j++) cur = __fadd_rn(cur, rj[j]);
-                t += nb;
-            } else {
+                    for (int j = 0; j < 4; j++) c = __fadd_rn(c, rj[j]);
+                    tt += nb;
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (j < nb) {
-                        const int code = (int)((codes >> (8 * j)) & 0xFFu);
-                        if (inr[j]) {
-                            if (code != live) {
-                                w_checkin<NM>(cur, live, acc);
-                                if (code != 0xFF) cur = w_checkout<NM>(code, live, acc);
-                            }
-                            const float a = aj[j];
-                            const float x = __fmaf_rn(a, dx, sx), y = __fmaf_rn(a, dy, sy), z = __fmaf_rn(a, dz, sz);
-                            if (code != 0xFF) {
-                                if (USE_TEX) {
-                                    cur = __fadd_rn(cur, rj[j]);
-                                } else if (STAGE_COEF) {
-                                    // cell-local coordinates: l = p - box_lo; exact for x >= 1
-                                    const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-                                    const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
-                                    const int idx = (int)__fmaf_rn(__fmaf_rn(fbz, (float)ny, fby), (float)nx, fbx);
-                                    const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
-                                    cur = __fadd_rn(cur, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                    for (int j = 0; j < 4; j++) {
+                        if (j < nb) {
+                            const int code = (int)((codes >> (8 * j)) & 0xFFu);
+                            if (inr[j]) {
+                                if (code != lv) {
+                                    w_checkin<NM>(c, lv, acc[0]);
+                                    if (code != 0xFF) c = w_checkout<NM>(code, lv, acc[0]);
                                 }
-                            } else {
-                                w_slow_sample<NM, USE_TEX>(vol, x, y, z, (t == 0 || t == last) ? 0.5f : 1.0f, acc, rj[j], USE_TEX);  // K.cu:537
+                                const float a = aj[j];
+                                const float x = __fmaf_rn(a, dxr, sx), y = __fmaf_rn(a, dyr, sy), z = __fmaf_rn(a, dzr, sz);
+                                if (code != 0xFF) {
+                                    if (USE_TEX) {
+                                        c = __fadd_rn(c, rj[j]);
+                                    } else if (STAGE_COEF) {
+                                        // cell-local coordinates: l = p - box_lo; exact for x >= 1
+                                        const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
+                                        const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                                        const int idx = min((int)__fmaf_rn(__fmaf_rn(fbz, (float)ny, fby), (float)nx, fbx), MAXC - 1);
+                                        const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
+                                        c = __fadd_rn(c, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                                    }
+                                } else {
+                                    w_slow_sample<NM, USE_TEX>(vol, x, y, z, (tt == 0 || tt == last) ? 0.5f : 1.0f, acc[0], rj[j], USE_TEX);  // K.cu:537
+                                }
                             }
+                            tt++;
                         }
-                        t++;
                     }
                 }
-            }
-            float a_last = aj[0];
+                float a_last = aj[0];
 #pragma unroll
-            for (int j = 1; j < 4; j++) a_last = (j < nb) ? aj[j] : a_last;
-            alpha = __fadd_rn(a_last, step);
+                for (int j = 1; j < 4; j++) a_last = (j < nb) ? aj[j] : a_last;
+                al = __fadd_rn(a_last, step);
+            }
+            alpha[0] = al; cur[0] = c; live[0] = lv;
+            rotate();
         }
+        t += S;
     }
-    w_checkin<NM>(cur, live, acc);
+#pragma unroll
+    for (int r = 0; r < R; r++) w_checkin<NM>(cur[r], live[r], acc[r]);
 }
 
-// Single-volume tile: per-lane ray set-up (K.cu:220-334), then the lock-step march.
-template <int NM, int KTEX>
-__device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, bool pixel_ok, float4* s_coef,
-                                           uint8_t* s_code, int lane, float* acc, unsigned long long& my_steps, unsigned long long& my_window) {
+// Single-volume tile: per-ray set-up (K.cu:220-334), then the lock-step march.  Lane l walks pixels (udx, vdx + 4 r), r < R.
+template <int NM, int KTEX, int R>
+__device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& vw, int udx, int vdx, float4* s_coef, uint8_t* s_code, int lane,
+                                           float (&acc)[R][NM], unsigned long long& my_steps, unsigned long long& my_window) {
     const VolDev& vol = P.vol[0];
-    float dx = 0.f, dy = 0.f, dz = 0.f, lo = 0.f, hi = -1.f, alpha = 0.f;
+    float dx[R], dy[R], dz[R], lo[R], hi[R], alpha[R];
+    int num_steps[R];
     const float sx = vw.src[0][0], sy = vw.src[0][1], sz = vw.src[0][2];
-    int num_steps = 0;
-    if (pixel_ok && P.enabled[0] != 0) {
-        Ray r = make_ray(vw.w2i, udx, vdx);
-        ray_dir_ijk(r, vw.ijk[0], dx, dy, dz);
-        if (slab_test(dx, dy, dz, sx, sy, sz, vol.ni, vol.nj, vol.nk, P.max_ray_length, lo, hi)) {
-            float minAlpha = fminf(r.ray_length, lo), maxAlpha = fmaxf(0.0f, hi);         // K.cu:242-244, 321-322
-            num_steps = (int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), P.step));  // K.cu:334
-            num_steps = max(num_steps, 0);
-            alpha = minAlpha;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        dx[r] = dy[r] = dz[r] = lo[r] = alpha[r] = 0.f; hi[r] = -1.f; num_steps[r] = 0;
+        const int v = vdx + TILE_H * r;
+        if (udx < P.W && v < P.H && P.enabled[0] != 0) {
+            Ray ry = make_ray(vw.w2i, udx, v);
+            ray_dir_ijk(ry, vw.ijk[0], dx[r], dy[r], dz[r]);
+            if (slab_test(dx[r], dy[r], dz[r], sx, sy, sz, vol.ni, vol.nj, vol.nk, P.max_ray_length, lo[r], hi[r])) {
+                float minAlpha = fminf(ry.ray_length, lo[r]), maxAlpha = fmaxf(0.0f, hi[r]);   // K.cu:242-244, 321-322
+                num_steps[r] = max((int)ceilf(__fdiv_rn(__fsub_rn(maxAlpha, minAlpha), P.step)), 0);  // K.cu:334
+                alpha[r] = minAlpha;
+            }
         }
+        my_steps += (unsigned)num_steps[r];
+        if (num_steps[r] > 0 && hi[r] >= lo[r])  // samples that fetch density: the steps whose alpha lies in [lo, hi] (to within one step)
+            my_window += (unsigned)min(num_steps[r], (int)__fdiv_rn(__fsub_rn(hi[r], fmaxf(lo[r], alpha[r])), P.step) + 1);
     }
-    my_steps += (unsigned)num_steps;
-    if (num_steps > 0 && hi >= lo)  // samples that fetch density: the steps whose alpha lies in [lo, hi] (to within one step)
-        my_window += (unsigned)min(num_steps, (int)__fdiv_rn(__fsub_rn(hi, fmaxf(lo, alpha)), P.step) + 1);
-    march_core<NM, KTEX, false>(vol, P.step, sx, sy, sz, dx, dy, dz, lo, hi, alpha, num_steps, s_coef, s_code, lane, acc);
+    march_core<NM, KTEX, false, R>(vol, P.step, sx, sy, sz, dx, dy, dz, lo, hi, alpha, num_steps, s_coef, s_code, lane, acc, P.slack_lo, P.slack_hi, P.slack_alpha);
 }
 
 template <int NM>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_kernel(const __grid_constant__ MarchParams P) {
+__global__ void __launch_bounds__(32 * SWB, SMB) march_warp_kernel(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
     uint8_t* s_code_alu = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
     uint8_t* s_code_tex = smem_raw + (size_t)warp * WARP_SMEM;
-    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+    constexpr int R = RAYS_PER_LANE;
+    const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H * R - 1) / (TILE_H * R);
     const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
     const size_t npix = (size_t)P.W * P.H;
@@ -569,25 +675,28 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_warp_k
         const unsigned view = tile / tiles_per_view;
         const unsigned tv = tile - view * tiles_per_view;
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
-        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
-        const bool ok = udx < P.W && vdx < P.H;
+        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * (TILE_H * R) + (lane >> 3);
         // every tile uses the same sampler mix, and the mix is a function of the step index only, so results do not
         // depend on scheduling
-        float acc[NM];
+        float acc[R][NM];
         const ViewDev& vw = P.views[view];
         switch (P.tex_eighths) {
-            case 0: march_tile<NM, 0>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
-            case 1: case 2: case 3:
-            case 4: march_tile<NM, 4>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
-            case 5: march_tile<NM, 5>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
-            case 6: march_tile<NM, 6>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
-            case 7: march_tile<NM, 7>(P, vw, udx, vdx, ok, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
-            default: march_tile<NM, 8>(P, vw, udx, vdx, ok, s_coef, s_code_tex, lane, acc, my_steps, my_window); break;
+            case 0: march_tile<NM, 0, R>(P, vw, udx, vdx, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 1: case 2:
+            case 3: march_tile<NM, 3, R>(P, vw, udx, vdx, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 4: march_tile<NM, 4, R>(P, vw, udx, vdx, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            case 5: case 6:
+            case 7: march_tile<NM, 5, R>(P, vw, udx, vdx, s_coef, s_code_alu, lane, acc, my_steps, my_window); break;
+            default: march_tile<NM, 8, R>(P, vw, udx, vdx, s_coef, s_code_tex, lane, acc, my_steps, my_window); break;
         }
-        if (ok) {
-            float* out = P.area + (size_t)view * P.M * npix + (size_t)vdx * P.W + udx;
 #pragma unroll
-            for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[m], step), 10.0f);  // K.cu:565-567, 582-584
+        for (int r = 0; r < R; r++) {
+            const int v = vdx + TILE_H * r;
+            if (udx < P.W && v < P.H) {
+                float* out = P.area + (size_t)view * P.M * npix + (size_t)v * P.W + udx;
+#pragma unroll
+                for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(__fmul_rn(acc[r][m], step), 10.0f);  // K.cu:565-567, 582-584
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -722,15 +831,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_
                 if (i == a) { dx = dxs[i]; dy = dys[i]; dz = dzs[i]; lo = los[i]; hi = his[i]; }
                 else if ((active >> i) & 1u) { olo = fminf(olo, los[i]); ohi = fmaxf(ohi, his[i]); }
             }
-            if (mesh_lo <= mesh_hi) { olo = fminf(olo, mesh_lo - 0.05f); ohi = fmaxf(ohi, mesh_hi + 0.05f); }
+            if (mesh_lo <= mesh_hi) { olo = fminf(olo, mesh_lo - 5.0f * P.slack_alpha); ohi = fmaxf(ohi, mesh_hi + 5.0f * P.slack_alpha); }
             const VolDev& vol = P.vol[a];
             const float sx = vw.src[a][0], sy = vw.src[a][1], sz = vw.src[a][2];
+            const float dx1[1] = {dx}, dy1[1] = {dy}, dz1[1] = {dz}, lo1[1] = {lo}, hi1[1] = {hi};
+            float al1[1] = {minAlpha};
+            const int ns1[1] = {num_steps};
+            float acc1[1][NM];
             if (P.tex_eighths <= 0)
-                march_core<NM, 0, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, tile, olo, ohi);
+                march_core<NM, 0, true, 1>(vol, step, sx, sy, sz, dx1, dy1, dz1, lo1, hi1, al1, ns1, s_coef, s_code_alu, lane, acc1, P.slack_lo, P.slack_hi, P.slack_alpha, &P, tile, olo, ohi);
             else if (P.tex_eighths >= 8)
-                march_core<NM, 8, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_tex, lane, acc, &P, tile, olo, ohi);
+                march_core<NM, 8, true, 1>(vol, step, sx, sy, sz, dx1, dy1, dz1, lo1, hi1, al1, ns1, s_coef, s_code_tex, lane, acc1, P.slack_lo, P.slack_hi, P.slack_alpha, &P, tile, olo, ohi);
             else
-                march_core<NM, 5, true>(vol, step, sx, sy, sz, dx, dy, dz, lo, hi, minAlpha, num_steps, s_coef, s_code_alu, lane, acc, &P, tile, olo, ohi);
+                march_core<NM, 5, true, 1>(vol, step, sx, sy, sz, dx1, dy1, dz1, lo1, hi1, al1, ns1, s_coef, s_code_alu, lane, acc1, P.slack_lo, P.slack_hi, P.slack_alpha, &P, tile, olo, ohi);
+#pragma unroll
+            for (int m = 0; m < NM; m++) acc[m] = acc1[0][m];
         }
         int view2, u2, v2;
         tile_pixel(P, tile, lane, view2, u2, v2);
@@ -792,14 +907,14 @@ cudaError_t drr_launch_march_multi(const MarchParams& P, int n_sm, cudaStream_t 
 // ---------------------------------------------------------------------------------------------
 template <int NM>
 static cudaError_t launch_warp_nm(const MarchParams& P, int n_sm, cudaStream_t s) {
-    const size_t smem = (size_t)WARP_SMEM * WARPS_PER_BLOCK;
+    const size_t smem = (size_t)WARP_SMEM * SWB;
     cudaError_t e = cudaFuncSetAttribute(march_warp_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_warp_kernel<NM>, 32 * WARPS_PER_BLOCK, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_warp_kernel<NM>, 32 * SWB, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    march_warp_kernel<NM><<<n_sm * occ, 32 * WARPS_PER_BLOCK, smem, s>>>(P);
+    march_warp_kernel<NM><<<n_sm * occ, 32 * SWB, smem, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -178,33 +178,34 @@ __global__ void __launch_bounds__(256) neglog_kernel(float* __restrict__ img, si
 // collected energy (K.cu:14-133, projector.py:833-853)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float solid_angle_px(const float* __restrict__ w, int udx, int vdx) {
+    // Explicit roundings: the contraction pattern nvcc gives the reference's calculate_solid_angle (read from the SASS of the
+    // unmodified kernel).  The result is a difference of nearly equal products, so a different pattern moves it by 1e-4 relative.
     float cx[4], cy[4], cz[4], cm[4];
     const float cu_off[4] = {0.f, 1.f, 1.f, 0.f}, cv_off[4] = {0.f, 0.f, 1.f, 1.f};
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        float cu = udx + cu_off[c], cv = vdx + cv_off[c];
-        cx[c] = cu * w[0] + cv * w[1] + w[2];
-        cy[c] = cu * w[3] + cv * w[4] + w[5];
-        cz[c] = cu * w[6] + cv * w[7] + w[8];
-        cm[c] = sqrtf((cx[c] * cx[c]) + (cy[c] * cy[c]) + (cz[c] * cz[c]));
+        const float cu = __fadd_rn((float)udx, cu_off[c]), cv = __fadd_rn((float)vdx, cv_off[c]);
+        cx[c] = __fadd_rn(__fmaf_rn(w[0], cu, __fmul_rn(w[1], cv)), w[2]);
+        cy[c] = __fadd_rn(__fmaf_rn(w[3], cu, __fmul_rn(w[4], cv)), w[5]);
+        cz[c] = __fadd_rn(__fmaf_rn(w[6], cu, __fmul_rn(w[7], cv)), w[8]);
+        cm[c] = __fsqrt_rn(__fmaf_rn(cz[c], cz[c], __fmaf_rn(cx[c], cx[c], __fmul_rn(cy[c], cy[c]))));
     }
-    float kx = (cy[0] * cz[2]) - (cz[0] * cy[2]);
-    float ky = (cz[0] * cx[2]) - (cx[0] * cz[2]);
-    float kz = (cx[0] * cy[2]) - (cy[0] * cx[2]);
-    float d01 = (cx[0] * cx[1]) + (cy[0] * cy[1]) + (cz[0] * cz[1]);
-    float d02 = (cx[0] * cx[2]) + (cy[0] * cy[2]) + (cz[0] * cz[2]);
-    float d03 = (cx[0] * cx[3]) + (cy[0] * cy[3]) + (cz[0] * cz[3]);
-    float d12 = (cx[1] * cx[2]) + (cy[1] * cy[2]) + (cz[1] * cz[2]);
-    float d23 = (cx[2] * cx[3]) + (cy[2] * cy[3]) + (cz[2] * cz[3]);
-    float n012 = fabsf((cx[1] * kx) + (cy[1] * ky) + (cz[1] * kz));
-    float n023 = fabsf((cx[3] * kx) + (cy[3] * ky) + (cz[3] * kz));
-    float e012 = (cm[0] * cm[1] * cm[2]) + (d01 * cm[2]) + (d02 * cm[1]) + (d12 * cm[0]);
-    float e023 = (cm[0] * cm[2] * cm[3]) + (d02 * cm[3]) + (d03 * cm[2]) + (d23 * cm[0]);
-    float s1 = 2.f * atan2f(n012, e012);
-    if (s1 < 0.0f) s1 += CUDART_PI_F;
-    float s2 = 2.f * atan2f(n023, e023);
-    if (s2 < 0.0f) s2 += CUDART_PI_F;
-    return s1 + s2;
+    auto dot = [&](int a, int b) { return __fmaf_rn(cz[a], cz[b], __fmaf_rn(cx[a], cx[b], __fmul_rn(cy[a], cy[b]))); };
+    const float kx = __fmaf_rn(cy[0], cz[2], -__fmul_rn(cz[0], cy[2]));
+    const float ky = __fmaf_rn(cz[0], cx[2], -__fmul_rn(cx[0], cz[2]));
+    const float kz = __fmaf_rn(cx[0], cy[2], -__fmul_rn(cy[0], cx[2]));
+    const float d01 = dot(0, 1), d02 = dot(0, 2), d03 = dot(0, 3), d12 = dot(1, 2), d23 = dot(2, 3);
+    const float n012 = fabsf(__fmaf_rn(cz[1], kz, __fmaf_rn(cx[1], kx, __fmul_rn(cy[1], ky))));
+    const float n023 = fabsf(__fmaf_rn(cz[3], kz, __fmaf_rn(cx[3], kx, __fmul_rn(cy[3], ky))));
+    const float e012 = __fmaf_rn(d12, cm[0], __fmaf_rn(d02, cm[1], __fmaf_rn(__fmul_rn(cm[1], cm[0]), cm[2], __fmul_rn(d01, cm[2]))));
+    const float e023 = __fmaf_rn(d23, cm[0], __fmaf_rn(d03, cm[2], __fmaf_rn(__fmul_rn(cm[2], cm[0]), cm[3], __fmul_rn(d02, cm[3]))));
+    float s1 = atan2f(n012, e012);
+    s1 = __fadd_rn(s1, s1);
+    if (s1 < 0.0f) s1 = __fadd_rn(s1, CUDART_PI_F);
+    float s2 = atan2f(n023, e023);
+    s2 = __fadd_rn(s2, s2);
+    if (s2 < 0.0f) s2 = __fadd_rn(s2, CUDART_PI_F);
+    return __fadd_rn(s1, s2);
 }
 
 // pass 1: solid angle per pixel + per-view sum (double); pass 2: scale the intensity

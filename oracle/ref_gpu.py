@@ -38,6 +38,8 @@ def _load():
                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_float)]
         lib.ref_destroy.argtypes = [ctypes.c_void_p]
+        lib.ref_want_solid.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.ref_fetch_solid.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.ref_set_mesh.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int]
         lib.ref_tide.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
         _lib = lib
@@ -109,6 +111,19 @@ class RefProjector:
         _chk(_load().ref_project(self.h, W, H, float(step), _p(pr), _p(en), _p(s), float(max_ray_length), _p(w), _p(a),
                                  threads, int(transpose), _p(inten), _p(pprob), ctypes.byref(ms)))
         return inten, pprob, ms.value
+
+    def solid_angle(self, W: int, H: int, w2i: np.ndarray, src_ijk: np.ndarray, ijk_from_world: np.ndarray, max_ray_length: float) -> np.ndarray:
+        """[H, W] solid angle per pixel as the reference kernel's ``calculate_solid_angle`` writes it
+        (project_kernel.cu:14-133, 213-216; a function of world_from_index and the pixel only)."""
+        assert self._spectrum is not None, "set_spectrum first (the kernel runs as a whole)"
+        _chk(_load().ref_want_solid(self.h, 1))
+        try:
+            self.project(W, H, 1.0e6, w2i, src_ijk, ijk_from_world, max_ray_length, fetch=False)  # huge step: the march is over at once
+            out = np.empty((H, W), dtype=np.float32)
+            _chk(_load().ref_fetch_solid(self.h, _p(out), 1))
+        finally:
+            _load().ref_want_solid(self.h, 0)
+        return out
 
     def line_integrals(self, W, H, step, w2i, src_ijk, ijk_from_world, max_ray_length, priority=None, enabled=None):
         """[M, H, W] per-material area densities (g/cm^2) straight from the reference's march."""

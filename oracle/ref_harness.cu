@@ -39,7 +39,8 @@ struct RefHarness {
     float *d_w2i = nullptr, *d_ijk = nullptr;
     float *d_energies = nullptr, *d_pdf = nullptr, *d_mu = nullptr;
     int n_bins = 0;
-    float *d_intensity = nullptr, *d_pprob = nullptr;
+    float *d_intensity = nullptr, *d_pprob = nullptr, *d_solid = nullptr;
+    bool want_solid = false;
     int out_w = 0, out_h = 0;
     // mesh dummies (the kernel reads mesh_sub_layer_valid[j] unconditionally)
     float *d_hit_alpha = nullptr;
@@ -215,9 +216,10 @@ int ref_project(void* hp, int W, int H, float step, const int* priority, const i
     int V = h->V;
     size_t npx = (size_t)W * H;
     if (h->out_w != W || h->out_h != H) {
-        if (h->d_intensity) { cudaFree(h->d_intensity); cudaFree(h->d_pprob); }
+        if (h->d_intensity) { cudaFree(h->d_intensity); cudaFree(h->d_pprob); cudaFree(h->d_solid); }
         RH_CHECK(cudaMalloc(&h->d_intensity, 4 * npx));
         RH_CHECK(cudaMalloc(&h->d_pprob, 4 * npx));
+        RH_CHECK(cudaMalloc(&h->d_solid, 4 * npx));
         h->out_w = W; h->out_h = H;
     }
     // projector.py:802-831 -- five small uploads per view (+ priorities/enabled, projector.py:674-675)
@@ -231,7 +233,9 @@ int ref_project(void* hp, int W, int H, float step, const int* priority, const i
     RH_CHECK(cudaMemcpy(h->d_priority, priority, 4 * V, cudaMemcpyHostToDevice));
     RH_CHECK(cudaMemcpy(h->d_enabled, enabled, 4 * V, cudaMemcpyHostToDevice));
 
-    void* solid = nullptr;
+    // project_kernel.cu:213-216: the kernel fills solid_angle when the pointer is non-null (projector.py:752 passes the
+    // buffer when collected_energy is set, else 0)
+    void* solid = h->want_solid ? (void*)h->d_solid : nullptr;
     int n_mesh_mats = h->n_mesh_mats, off = 0;
     void* args[] = {&h->d_vol_tex, &h->d_seg_tex, &W, &H, &step, &h->d_priority, &h->d_enabled,
                     &h->d_min[0], &h->d_min[1], &h->d_min[2], &h->d_max[0], &h->d_max[1], &h->d_max[2],
@@ -300,11 +304,28 @@ int ref_destroy(void* hp) {
     cudaFree(h->d_vol_tex); cudaFree(h->d_seg_tex); cudaFree(h->d_priority); cudaFree(h->d_enabled);
     for (int a = 0; a < 3; a++) { cudaFree(h->d_min[a]); cudaFree(h->d_max[a]); cudaFree(h->d_vox[a]); cudaFree(h->d_src[a]); }
     cudaFree(h->d_w2i); cudaFree(h->d_ijk); cudaFree(h->d_energies); cudaFree(h->d_pdf); cudaFree(h->d_mu);
-    cudaFree(h->d_intensity); cudaFree(h->d_pprob); cudaFree(h->d_layer_valid); cudaFree(h->d_hit_alpha);
+    cudaFree(h->d_intensity); cudaFree(h->d_pprob); cudaFree(h->d_solid); cudaFree(h->d_layer_valid); cudaFree(h->d_hit_alpha);
     cudaFree(h->d_hit_facing); cudaFree(h->d_additive); cudaFree(h->d_mesh_mats);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     if (h->mod) cuModuleUnload(h->mod);
     delete h;
+    return 0;
+}
+
+// Ask the next ref_project calls to pass a solid_angle buffer, and read it back: raw kernel layout [W][H]
+// (index udx * H + vdx, project_kernel.cu:208) or, with `transpose`, [H][W] like the images.
+int ref_want_solid(void* hp, int on) { ((RefHarness*)hp)->want_solid = on != 0; return 0; }
+
+int ref_fetch_solid(void* hp, float* out, int transpose) {
+    RefHarness* h = (RefHarness*)hp;
+    if (!h->d_solid || !h->want_solid) { g_err = "ref_fetch_solid: no solid-angle buffer (call ref_want_solid and ref_project first)"; return -1; }
+    const int W = h->out_w, H = h->out_h;
+    const size_t npx = (size_t)W * H;
+    if (!transpose) { RH_CHECK(cudaMemcpy(out, h->d_solid, 4 * npx, cudaMemcpyDeviceToHost)); return 0; }
+    std::vector<float> tmp(npx);
+    RH_CHECK(cudaMemcpy(tmp.data(), h->d_solid, 4 * npx, cudaMemcpyDeviceToHost));
+    for (int u = 0; u < W; u++)
+        for (int v = 0; v < H; v++) out[(size_t)v * W + u] = tmp[(size_t)u * H + v];
     return 0;
 }
 

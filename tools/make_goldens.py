@@ -57,8 +57,38 @@ def run_case(name, volumes, projs, max_ray_length, spectrum, step=0.1, sub=1, pr
     refl.close()
 
 
+def solid_angle_case():
+    """calculate_solid_angle of the reference kernel (project_kernel.cu:14-133, reached with a non-null solid_angle pointer,
+    :213-216) for a few cameras: the C1 views, an oblique MobileCArm pose on a non-square sensor, and a strongly off-centre one."""
+    v = phantoms.c1_volume(16)
+    st = SceneTables([v], "90KV_AL40")
+    ref = RefProjector([v.data], st.labels, st.M, [v.spacing])
+    ref.set_spectrum(st.energies, st.pdf, st.mu)
+    cams = []
+    for d in ((0.3, 1.0, 0.2), (0.0, 1.0, 0.0), (1.0, 0.0, 1.0)):
+        p, mrl = phantoms.c1_camera(direction=d)
+        cams.append((p, mrl))
+    carm = phantoms.MobileCArmGeometry(sensor_width=192, sensor_height=160, pixel_size=1.5)
+    cams.append((carm.camera_projection(0.5, -0.4, (10.0, -20.0, 5.0)), carm.max_ray_length))
+    k = geo.CameraIntrinsicTransform(np.array([[900.0, 0, 20.0], [0, 1100.0, 150.0], [0, 0, 1]]), sensor_height=120, sensor_width=100)
+    cams.append((phantoms.look_at_projection((100.0, -700.0, 50.0), (-0.1, 1.0, 0.0), (0, 0, 1), k), 3000.0))
+    rec = {}
+    for i, (p, mrl) in enumerate(cams):
+        W, H = p.intrinsic.sensor_size
+        w2i, src, a = geo.pose_arrays(p, [v])
+        rec[f"w2i_{i}"], rec[f"W_{i}"], rec[f"H_{i}"] = w2i, W, H
+        rec[f"solid_{i}"] = ref.solid_angle(W, H, w2i, src, a, mrl)
+        print(f"[golden] solid angle view {i}: {W}x{H}, mean {rec[f'solid_{i}'].mean():.6e}", flush=True)
+    ref.close()
+    np.savez_compressed(os.path.join(OUT, "solid_angle.npz"), **rec)
+
+
 def main():
     t0 = time.time()
+    if "--solid-only" in sys.argv:
+        solid_angle_case()
+        return
+    solid_angle_case()
     # C1 (SURVEY 8(d)): 128^3 cylinder, 256^2, 90 kV; plus an axis-aligned view (zero direction components)
     v1 = phantoms.c1_volume()
     p1, mrl1 = phantoms.c1_camera()
