@@ -985,11 +985,13 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         }
         c->launches += 1;
     } else {
-        if (V > 4 || M > 8) return fail(c, DRR_E_INVALID, "drr_project: the general kernel supports up to 4 volumes / 8 materials");
+        if (V > DRR_MAX_VOLUMES || M > DRR_MAX_MATERIALS)
+            return fail(c, DRR_E_INVALID, "drr_project: at most %d volumes / %d materials", DRR_MAX_VOLUMES, DRR_MAX_MATERIALS);
         for (int v = 0; v < V; v++)
             if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_project: volume %d has no raw arrays", v);
         // Tiles whose rays see a single volume take the lock-step kernel; the others are listed for the general one.
-        bool split = !c->attenuate_outside && c->variant == 0 && lockstep_ok;  // (V == 1 gets here only with meshes)
+        // (V == 1 gets here only with meshes or more than 8 materials; the lock-step kernels are built for V <= 4, M <= 8)
+        bool split = !c->attenuate_outside && c->variant == 0 && lockstep_ok && V <= 4 && M <= 8;
         int sampler = c->sampler;
         for (int v = 0; v < V; v++)  // a volume without coefficient records: texture unit only; without a texture: FMA pipes only
             if (!c->vols[v].cellc && c->vols[v].tex) sampler = DRR_SAMPLER_TEX;

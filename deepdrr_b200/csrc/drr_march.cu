@@ -215,8 +215,12 @@ __global__ void __launch_bounds__(256) march_single_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // general path: NV volumes, priorities, meshes, outside air
 // ---------------------------------------------------------------------------------------------
+// (NV, NM) are compile-time sizes of the per-ray register arrays.  Instantiated for every (V, M) up to 4 x 8 and once more "wide"
+// as (DRR_MAX_VOLUMES, DRR_MAX_MATERIALS) for scenes beyond that, where the actual counts are read from P at run time -- the
+// reference compiles its kernel for any -D NUM_VOLUMES / NUM_MATERIALS (projector.py:365-386).
 template <int NV, int NM>
 __device__ __forceinline__ void general_ray(const MarchParams& P, const int view, const int udx, const int vdx) {
+    constexpr bool WIDE = NV > 4 || NM > 8;
     const ViewDev& vw = P.views[view];
     const size_t npix = (size_t)P.W * P.H;
     const size_t pix = (size_t)vdx * P.W + udx;
@@ -233,6 +237,7 @@ __device__ __forceinline__ void general_ray(const MarchParams& P, const int view
     for (int i = 0; i < NV; i++) {
         dx[i] = dy[i] = dz[i] = 0.0f; lo[i] = hi[i] = 0.0f;
         trace[i] = false;
+        if (WIDE && i >= P.V) continue;  // the wide instantiation serves any V <= NV
         if (P.enabled[i] == 0) continue;
         ray_dir_ijk(r, vw.ijk[i], dx[i], dy[i], dz[i]);
         trace[i] = slab_test(dx[i], dy[i], dz[i], vw.src[i][0], vw.src[i][1], vw.src[i][2], P.vol[i].ni, P.vol[i].nj, P.vol[i].nk,
@@ -264,6 +269,7 @@ __device__ __forceinline__ void general_ray(const MarchParams& P, const int view
         int curr_priority = NV, n_at = 0;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
+            if (WIDE && i >= P.V) continue;
             if (!trace[i] || P.enabled[i] == 0) continue;
             if (alpha < lo[i] || alpha > hi[i]) continue;
             if (P.priority[i] < curr_priority) { curr_priority = P.priority[i]; n_at = 1; }
@@ -289,6 +295,7 @@ __device__ __forceinline__ void general_ray(const MarchParams& P, const int view
         }
 #pragma unroll
         for (int i = 0; i < NV; i++) {
+            if (WIDE && i >= P.V) continue;  // (a volume that does not exist must not touch the shared label cache either)
             const VolDev& vol = P.vol[i];
             float px = __fsub_rn(__fmaf_rn(alpha, dx[i], vw.src[i][0]), 1.0f);
             float py = __fsub_rn(__fmaf_rn(alpha, dy[i], vw.src[i][1]), 1.0f);
@@ -358,9 +365,10 @@ __device__ __forceinline__ void general_ray(const MarchParams& P, const int view
     }
     float* out = P.area + (size_t)view * P.M * npix + pix;
 #pragma unroll
-    for (int m = 0; m < NM; m++) out[(size_t)m * npix] = __fdiv_rn(area[m], 10.0f);  // K.cu:582-584
+    for (int m = 0; m < NM; m++)
+        if (!WIDE || m < P.M) out[(size_t)m * npix] = __fdiv_rn(area[m], 10.0f);  // K.cu:582-584
     // S_view bookkeeping
-    unsigned long long ns = num_steps > 0 ? (unsigned long long)num_steps * NV : 0ull;
+    unsigned long long ns = num_steps > 0 ? (unsigned long long)num_steps * (WIDE ? P.V : NV) : 0ull;
     unsigned mask = __activemask();
     for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(mask, ns, o);
     if ((threadIdx.x & 31) == (__ffs(mask) - 1) && ns) atomicAdd(P.sample_count, ns);
@@ -491,6 +499,7 @@ static cudaError_t launch_general_list_nv(const MarchParams& P, int grid, cudaSt
 }
 
 cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaStream_t s) {
+    if (P.V > 4 || P.M > 8) return launch_general_list_nvnm<DRR_MAX_VOLUMES, DRR_MAX_MATERIALS>(P, grid, s);
     switch (P.V) {
         case 1: return launch_general_list_nv<1>(P, grid, s);
         case 2: return launch_general_list_nv<2>(P, grid, s);
@@ -501,6 +510,7 @@ cudaError_t drr_launch_march_general_list(const MarchParams& P, int grid, cudaSt
 }
 
 cudaError_t drr_launch_march_general(const MarchParams& P, cudaStream_t s) {
+    if (P.V > 4 || P.M > 8) return launch_general_nvnm<DRR_MAX_VOLUMES, DRR_MAX_MATERIALS>(P, s);
     switch (P.V) {
         case 1: return launch_general_nv<1>(P, s);
         case 2: return launch_general_nv<2>(P, s);

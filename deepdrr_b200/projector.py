@@ -159,6 +159,11 @@ class Projector(object):
         self.air_index = air_index
         self.attenuate_outside_volume = attenuate_outside_volume
 
+        # limits of the library (include/drr_b200.h); the reference compiles its kernel for any count (projector.py:365-386)
+        if len(self.volumes) > _lib.MAX_VOLUMES:
+            raise ValueError(f"at most {_lib.MAX_VOLUMES} volumes are supported, got {len(self.volumes)}")
+        if len(self.all_materials) > _lib.MAX_MATERIALS:
+            raise ValueError(f"at most {_lib.MAX_MATERIALS} materials are supported, got {len(self.all_materials)}: {self.all_materials}")
         for mat in self.all_materials:
             try:
                 Material.from_string(mat)

@@ -119,3 +119,88 @@ def test_fine_grid_far_source_single_volume_vs_live_reference(spacing, distance)
                 area = p.project_line_integrals(pose, max_ray_length=distance + 500.0)
             _check(area[0], None, li, None, f"wire {spacing} mm from {distance} mm [{sampler}] dir {direction}")
     refl.close()
+
+
+def test_five_volumes_vs_live_reference():
+    """More volumes than the lock-step kernels are built for (4): the step-by-step kernel's wide instantiation
+    (csrc/drr_march.cu, DRR_MAX_VOLUMES x DRR_MAX_MATERIALS register arrays, counts read at run time) against the reference
+    compiled with -D NUM_VOLUMES=5 (projector.py:365-386 compiles for any count)."""
+    ref_gpu = _ref()
+    ct = phantoms.thorax_volume((96, 96, 80), (4.2, 4.2, 5.0), seed=2)
+    wires = []
+    for tip, axis in (((-30.0, -40.0, 5.0), (0.3, 1.0, 0.1)), ((20.0, -50.0, -10.0), (-0.2, 1.0, 0.0)), ((0.0, -30.0, 25.0), (0.0, 1.0, -0.3)),
+                      ((-10.0, -45.0, -20.0), (0.5, 1.0, 0.4))):
+        w = phantoms.kwire_volume(length_mm=70.0, spacing=0.3, half_width=5)
+        phantoms.place_kwire(w, tip, axis)
+        wires.append(w)
+    volumes = [ct] + wires
+    for priorities in (None, [4, 0, 3, 1, 2]):
+        st = cases.tables(volumes, "90KV_AL40", priorities)
+        poses, sdd = phantoms.cone_poses(2, seed=9, sensor=144, pixel=0.8)
+        refl = ref_gpu.RefProjector([v.data for v in volumes], st.labels, st.M, lineint=True)
+        with Projector(volumes, priorities=priorities, spectrum="90KV_AL40", neglog=False, camera_intrinsics=poses[0].intrinsic,
+                       source_to_detector_distance=sdd) as p:
+            area = p.project_line_integrals(*poses)
+            mrl = p.max_ray_length
+        for n, pose in enumerate(poses):
+            w2i, src, ijk = geo.pose_arrays(pose, volumes)
+            li = refl.line_integrals(144, 144, 0.1, w2i, src, ijk, mrl, priority=st.priorities)
+            assert (li[st.all_materials.index("iron")] > 0).sum() > 100
+            _check(area[n], None, li, None, f"five volumes, priorities {priorities}, view {n}")
+        refl.close()
+
+
+def test_nine_materials_vs_live_reference():
+    """More materials than the templated kernels cover (8): one volume segmented into nine materials, reference compiled with
+    -D NUM_MATERIALS=9."""
+    from deepdrr_b200.vol import Volume
+
+    ref_gpu = _ref()
+    names = ["air", "blood", "bone", "concrete", "copper", "iron", "lung", "muscle", "soft tissue"]
+    rng = np.random.default_rng(5)
+    shape = (40, 36, 30)
+    # blobs of materials: labels vary smoothly enough for uniform cells to exist, densities are noisy
+    ii, jj, kk = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    labels = ((ii // 7 + 2 * (jj // 6) + 3 * (kk // 8)) % 9).astype(np.uint16)
+    data = (0.5 + 0.2 * labels + rng.normal(0, 0.03, shape)).astype(np.float32).clip(0.0, None)
+    a = np.diag([3.0, 3.0, 4.0, 1.0])
+    a[:3, 3] = [-3.0 * (shape[0] - 1) / 2, -3.0 * (shape[1] - 1) / 2, -4.0 * (shape[2] - 1) / 2]
+    vol = Volume(data, ({n: i for i, n in enumerate(names)}, labels), anatomical_from_IJK=geo.FrameTransform(a))
+    st = cases.tables([vol], "90KV_AL40", None)
+    assert st.M == 9
+    carm = phantoms.MobileCArmGeometry(sensor_width=120, sensor_height=96, pixel_size=1.6)
+    poses = phantoms.c2_poses(2, seed=21, carm=carm)
+    refl = ref_gpu.RefProjector([vol.data], st.labels, st.M, lineint=True)
+    refp = ref_gpu.RefProjector([vol.data], st.labels, st.M)
+    refp.set_spectrum(st.energies, st.pdf, st.mu)
+    with Projector(vol, spectrum="90KV_AL40", neglog=False, camera_intrinsics=carm.camera_intrinsics) as p:
+        area = p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length)
+        img = p.project(*poses, max_ray_length=carm.max_ray_length)
+    for n, pose in enumerate(poses):
+        w2i, src, ijk = geo.pose_arrays(pose, [vol])
+        li = refl.line_integrals(120, 96, 0.1, w2i, src, ijk, carm.max_ray_length)
+        ri, _, _ = refp.project(120, 96, 0.1, w2i, src, ijk, carm.max_ray_length)
+        assert sum(int((li[m] > 0).any()) for m in range(9)) == 9
+        _check(area[n], img[n], li, ri, f"nine materials view {n}")
+    refl.close(); refp.close()
+
+
+def test_limits_are_the_header_limits():
+    """include/drr_b200.h: DRR_MAX_VOLUMES 8, DRR_MAX_MATERIALS 16.  Beyond them the library says so when the volume / spectrum is
+    handed over, not at the first projection."""
+    from deepdrr_b200.vol import Volume
+    from deepdrr_b200 import _lib
+
+    tiny = np.ones((4, 4, 4), dtype=np.float32)
+    vols = []
+    for i in range(_lib.MAX_VOLUMES + 1):
+        v = Volume(tiny, ({"bone": 0}, np.zeros(tiny.shape, np.uint16)))
+        v.translate((6.0 * i, 0.0, 0.0))
+        vols.append(v)
+    k = geo.CameraIntrinsicTransform.from_sizes((16, 16), 1.0, 1000.0)
+    with pytest.raises(ValueError):
+        Projector(vols, camera_intrinsics=k).initialize()
+    with Projector(vols[:8], camera_intrinsics=k, neglog=False) as p:            # eight volumes do run
+        pose = phantoms.look_at_projection((20.0, -300.0, 0.0), (0, 1.0, 0), (0, 0, 1), k)
+        a = p.project_line_integrals(pose, max_ray_length=2000.0)
+        assert a.shape == (1, 1, 16, 16) and a.max() > 0

@@ -76,7 +76,13 @@ def test_config4_real_screw_over_ct_matches_restatement():
     checked against a float64 ray-triangle restatement of the GL semantics; every other material must equal
     the projection of the CT alone, since an additive mesh changes nothing in the march (K.cu:569-579)."""
     screw = _mesh("screw", 1.0, material="titanium")
-    phantoms.place_kwire(screw, (-25.0, -70.0, 5.0), (0.25, 1.0, 0.1))
+    # the STL's long axis is its local y (0 .. 130 mm): tilt it in the detector plane of the views (which look along ~ +z) and put
+    # the threaded end in the field of view (57 mm wide at the isocentre)
+    ax = np.array([0.8, 0.55, 0.25]) / np.linalg.norm([0.8, 0.55, 0.25])
+    e1 = np.cross(ax, [0.0, 0.0, 1.0]); e1 /= np.linalg.norm(e1)
+    rot = np.stack([e1, ax, np.cross(e1, ax)], axis=1)                  # local x, y, z -> world
+    tip_local = np.array([4.1, 0.0, 4.1])                               # on the screw's axis, at its y = 0 end
+    screw.world_from_anatomical = geo.FrameTransform.from_rt(rot, np.array([-14.0, -9.0, 3.0]) - rot @ tip_local)
     ct = phantoms.thorax_volume((128, 128, 100), (3.2, 3.2, 4.0))
     poses, sdd = phantoms.cone_poses(2, seed=4)
     k = poses[0].intrinsic
