@@ -241,20 +241,43 @@ class MobileCArm(Device):
         if device_in_world is not None:
             self.world_from_device = geo.FrameTransform.from_translation(np.asarray(device_in_world, dtype=np.float64).reshape(3))
 
+    def camera3d_from_world_batch(self, alphas: Sequence[float], betas: Sequence[float], isocenters: Optional[np.ndarray] = None,
+                                  degrees: bool = True) -> np.ndarray:
+        """``camera3d_from_world`` [n, 4, 4] for n poses at once -- the product ``gamma_rotation @ camera3d_from_arm @ arm_from_device @
+        device_from_world`` of the reference (device/mobile_carm.py:223-276) on stacked arrays, no per-view Python loop:
+        device_from_arm = [Ry(beta) Rx(alpha) | isocenter] (scipy ``from_euler("xy")``), whose inverse is [R^T | -R^T isocenter]."""
+        al = np.asarray([_radians(float(a), degrees) for a in alphas], dtype=np.float64) if not isinstance(alphas, np.ndarray) \
+            else (np.deg2rad(alphas.astype(np.float64)) if degrees else alphas.astype(np.float64))
+        be = np.asarray([_radians(float(b), degrees) for b in betas], dtype=np.float64) if not isinstance(betas, np.ndarray) \
+            else (np.deg2rad(betas.astype(np.float64)) if degrees else betas.astype(np.float64))
+        n = al.shape[0]
+        iso = np.broadcast_to(self.isocenter, (n, 3)) if isocenters is None else np.asarray(isocenters, dtype=np.float64).reshape(n, 3)
+        ca, sa, cb, sb = np.cos(al), np.sin(al), np.cos(be), np.sin(be)
+        zero, one = np.zeros(n), np.ones(n)
+        rx = np.stack([np.stack([one, zero, zero], -1), np.stack([zero, ca, -sa], -1), np.stack([zero, sa, ca], -1)], -2)
+        ry = np.stack([np.stack([cb, zero, sb], -1), np.stack([zero, one, zero], -1), np.stack([-sb, zero, cb], -1)], -2)
+        rt = np.transpose(ry @ rx, (0, 2, 1))                                       # R^T
+        arm_from_device = np.zeros((n, 4, 4))
+        arm_from_device[:, :3, :3] = rt
+        arm_from_device[:, :3, 3] = -(rt @ iso[:, :, None])[:, :, 0]
+        arm_from_device[:, 3, 3] = 1.0
+        cam_from_arm = np.eye(4)
+        cam_from_arm[:3, 3] = [0, -self.source_to_isocenter_horizontal_offset, self.source_to_isocenter_vertical_distance]
+        if self.rotate_camera_left:
+            rz = np.eye(4)
+            rz[:3, :3] = [[0, -1, 0], [1, 0, 0], [0, 0, 1]]
+            cam_from_arm = rz @ cam_from_arm
+        g = np.eye(4)
+        cg, sg = math.cos(self.gamma), math.sin(self.gamma)
+        g[:3, :3] = [[cg, -sg, 0], [sg, cg, 0], [0, 0, 1]]
+        return (g @ cam_from_arm)[None] @ arm_from_device @ self.device_from_world.data[None]
+
     def camera_projections(self, alphas: Sequence[float], betas: Sequence[float], isocenters: Optional[np.ndarray] = None,
                            degrees: bool = True) -> List[geo.CameraProjection]:
-        """A batch of poses without touching the device state (angles are NOT clipped to the device limits)."""
-        n = len(alphas)
-        iso = np.broadcast_to(self.isocenter, (n, 3)) if isocenters is None else np.asarray(isocenters, dtype=np.float64).reshape(n, 3)
+        """A batch of poses without touching the device state (angles are NOT clipped to the device limits).  The matrices come
+        from one stacked computation (``camera3d_from_world_batch``); only the thin ``CameraProjection`` wrappers are made per view."""
         k = self.camera_intrinsics
-        dfw = self.device_from_world.data
-        out = []
-        for i in range(n):
-            m = self._camera3d_from_device(_radians(alphas[i], degrees), _radians(betas[i], degrees), self.gamma, iso[i],
-                                           self.source_to_isocenter_vertical_distance, self.source_to_isocenter_horizontal_offset,
-                                           self.rotate_camera_left)
-            out.append(geo.CameraProjection(k, geo.FrameTransform(m @ dfw)))
-        return out
+        return [geo.CameraProjection(k, geo.FrameTransform(m)) for m in self.camera3d_from_world_batch(alphas, betas, isocenters, degrees)]
 
     def __str__(self):
         return f"MobileCArm(isocenter={np.array_str(self.isocenter)}, alpha={math.degrees(self.alpha)}, beta={math.degrees(self.beta)}, degrees=True)"

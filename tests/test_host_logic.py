@@ -172,3 +172,59 @@ def test_hu_volume_is_lazy_and_equivalent_on_the_host():
     assert Projector(a, camera_intrinsics=geo.CameraIntrinsicTransform.from_sizes((8, 8), 1.0, 100.0)).all_materials == ["air", "bone", "soft tissue"]
     assert a._host is None                                                          # nothing materialised so far
     assert np.array_equal(a.data, b.data) and np.array_equal(np.asarray(a.materials[1]), b.materials[1])
+
+
+def test_carm_poses_against_matrices_derived_from_the_reference_formulas():
+    """device/mobile_carm.py:223-258, written out with scipy exactly as the reference writes it (independent of this package's
+    code) and by hand for the poses where the matrices are obvious; the batched generator must reproduce both, for every view,
+    and hand the Projector the same kernel arrays as the per-view path."""
+    from scipy.spatial.transform import Rotation
+
+    from deepdrr_b200 import device
+
+    def reference(alpha, beta, gamma, iso, vertical, horizontal, left, world_from_device):
+        def rt(r=None, t=None):
+            m = np.eye(4)
+            if r is not None:
+                m[:3, :3] = r
+            if t is not None:
+                m[:3, 3] = t
+            return m
+        device_from_arm = rt(Rotation.from_euler("xy", [alpha, beta]).as_matrix(), iso)                 # :223-227
+        camera3d_from_arm = rt(t=[0, -horizontal, vertical])                                            # :239-245
+        if left:
+            camera3d_from_arm = rt(Rotation.from_euler("z", 90, degrees=True).as_matrix()) @ camera3d_from_arm   # :246-250
+        gamma_rotation = rt(Rotation.from_euler("z", gamma, degrees=False).as_matrix())                 # :255-257
+        return gamma_rotation @ camera3d_from_arm @ np.linalg.inv(device_from_arm) @ np.linalg.inv(world_from_device)  # :259, :276
+
+    wfd = geo.FrameTransform.from_rt(Rotation.from_euler("zyx", [0.3, -0.2, 0.1]).as_matrix(), (12.0, -7.0, 3.0))
+    c = device.MobileCArm(world_from_device=wfd, gamma=0.15, degrees=False, source_to_isocenter_horizontal_offset=4.0)
+    rng = np.random.default_rng(3)
+    n = 300
+    al, be = rng.uniform(-1.5, 1.5, n), rng.uniform(-1.5, 1.5, n)
+    iso = rng.uniform(-80, 80, (n, 3))
+    batch = c.camera3d_from_world_batch(al, be, iso, degrees=False)
+    assert batch.shape == (n, 4, 4)
+    for i in range(n):
+        want = reference(al[i], be[i], 0.15, iso[i], 530.0, 4.0, True, wfd.data)
+        assert np.allclose(batch[i], want, atol=1e-9), i
+    # by hand: no rotation, isocentre at the origin -> the source sits 530 mm below, the camera is turned 90 degrees about z
+    plain = device.MobileCArm()
+    m0 = plain.camera3d_from_world_batch([0.0], [0.0], None)[0]
+    assert np.allclose(m0, [[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 530.0], [0, 0, 0, 1]], atol=1e-12)
+    # alpha = 90 degrees about x: arm_from_device = Rx(-90): (x, y, z) -> (x, z, -y); then + (0, 0, 530), then Rz(90)
+    m1 = plain.camera3d_from_world_batch([90.0], [0.0], None)[0]
+    assert np.allclose(m1, [[0, 0, -1, 0], [1, 0, 0, 0], [0, -1, 0, 530.0], [0, 0, 0, 1]], atol=1e-12)
+    # beta = 90 degrees about y with the isocentre at (10, 0, 0): arm = Ry(-90) (p - iso): (x, y, z) -> (-z, y, x - 10)
+    m2 = plain.camera3d_from_world_batch([0.0], [90.0], np.array([[10.0, 0, 0]]))[0]
+    assert np.allclose(m2, [[0, -1, 0, 0], [0, 0, -1, 0], [1, 0, 0, 520.0], [0, 0, 0, 1]], atol=1e-12)
+    # the objects built from the batch equal the stateful per-view path, and so do the kernel arrays the Projector uploads
+    projs = c.camera_projections(al[:5], be[:5], iso[:5], degrees=False)
+    vol_ = phantoms.thorax_volume((8, 8, 6), (40.0, 40.0, 60.0))
+    w_b, s_b, a_b = geo.pose_arrays_batch(projs, [vol_])
+    for i in range(5):
+        c.move_to(isocenter=iso[i], alpha=al[i], beta=be[i], degrees=False)
+        one = c.get_camera_projection()
+        assert np.allclose(one.camera3d_from_world.data, projs[i].camera3d_from_world.data, atol=1e-9)
+        w1, s1, a1 = geo.pose_arrays(projs[i], [vol_])
+        assert np.array_equal(w1, w_b[i]) and np.array_equal(s1, s_b[i]) and np.array_equal(a1, a_b[i])
