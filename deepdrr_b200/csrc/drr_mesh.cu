@@ -120,6 +120,20 @@ __device__ __forceinline__ bool prim_misses_tile(const int* __restrict__ pb, int
     return pb[0] > u1 || pb[1] < u0 || pb[2] > v1 || pb[3] < v0;
 }
 
+// Distance of a hit.  Moeller-Trumbore's own t = (e2 . q) / det takes q = s x e1 with |s| ~ 500 mm against sub-millimetre edges; on
+// the sliver triangles of CAD meshes (the reference's 6.5 mm screw STL) that is 1.5e-2 mm off at the 90th percentile and 0.14 mm at
+// worst in fp32.  A hit is rare (a few per ray against thousands of candidate triangles), so its distance is taken from the
+// triangle's plane in double precision instead: t = n . (v0 - o) / n . d with n = e1 x e2 -- exact to the fp32 inputs (1e-5 mm),
+// then rounded to the float the buffers hold.  Out of line: the fp64 code must not be if-converted into the per-candidate path.
+__device__ __noinline__ float hit_distance(const float3& o, const float3& d, const float* __restrict__ v, float t_mt) {
+    const double e1x = (double)v[3] - v[0], e1y = (double)v[4] - v[1], e1z = (double)v[5] - v[2];
+    const double e2x = (double)v[6] - v[0], e2y = (double)v[7] - v[1], e2z = (double)v[8] - v[2];
+    const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+    const double num = nx * ((double)v[0] - o.x) + ny * ((double)v[1] - o.y) + nz * ((double)v[2] - o.z);
+    const double den = nx * d.x + ny * d.y + nz * d.z;
+    return den != 0.0 ? (float)(num / den) : t_mt;
+}
+
 // Moeller-Trumbore, double sided.  Returns true and (t, entering) for t > 0.
 __device__ __forceinline__ bool ray_tri(const float3& o, const float3& d, const float* __restrict__ v, float& t, bool& entering) {
     const float3 e1 = make_float3(v[3] - v[0], v[4] - v[1], v[5] - v[2]);
@@ -134,17 +148,7 @@ __device__ __forceinline__ bool ray_tri(const float3& o, const float3& d, const 
     const float3 q = make_float3(s.y * e1.z - s.z * e1.y, s.z * e1.x - s.x * e1.z, s.x * e1.y - s.y * e1.x);
     const float w = (d.x * q.x + d.y * q.y + d.z * q.z) * inv;
     if (w < 0.0f || u + w > 1.0f) return false;
-    // Distance: Moeller-Trumbore's own t = (e2 . q) / det takes q = s x e1 with |s| ~ 500 mm against sub-millimetre edges; on the
-    // sliver triangles of CAD meshes (the reference's 6.5 mm screw STL) that is 1.5e-2 mm off at the 90th percentile and 0.14 mm at
-    // worst in fp32.  A hit is rare (a few per ray), so its distance is taken from the triangle's plane in double precision instead:
-    // t = n . (v0 - o) / n . d with n = e1 x e2 -- exact to the fp32 inputs (1e-5 mm), then rounded to the float the buffers hold.
-    {
-        const double nx = (double)e1.y * e2.z - (double)e1.z * e2.y, ny = (double)e1.z * e2.x - (double)e1.x * e2.z,
-                     nz = (double)e1.x * e2.y - (double)e1.y * e2.x;
-        const double num = nx * ((double)v[0] - o.x) + ny * ((double)v[1] - o.y) + nz * ((double)v[2] - o.z);
-        const double den = nx * d.x + ny * d.y + nz * d.z;
-        t = den != 0.0 ? (float)(num / den) : (e2.x * q.x + e2.y * q.y + e2.z * q.z) * inv;
-    }
+    t = hit_distance(o, d, v, (e2.x * q.x + e2.y * q.y + e2.z * q.z) * inv);
     // geometric normal n = e1 x e2; det = d . (e1 x e2) ... sign(det) = sign(-d.n)?  p = d x e2, det = e1.(d x e2) = -d.(e1 x e2)
     entering = det > 0.0f;  // d . n < 0: the ray enters through an outward-facing (CCW) triangle
     return t > 0.0f;
