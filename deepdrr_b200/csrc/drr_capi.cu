@@ -67,8 +67,11 @@ struct ScatterTables {
 };
 struct ScatterParams {
     ScatterTables T;
-    VolDev vol;
-    float ijk[12];
+    int V;
+    int priority[DRR_MAX_VOLUMES];
+    int enabled[DRR_MAX_VOLUMES];
+    VolDev vol[DRR_MAX_VOLUMES];
+    float ijk[DRR_MAX_VOLUMES][12];
     float p_idx[12];
     float w2i[9];
     float src[3];
@@ -666,7 +669,10 @@ int drr_scatter(drr_ctx* c, unsigned long long n_photons, unsigned long long pho
                 double* out_counters, int out_mem_kind) {
     if (!c) return DRR_E_INVALID;
     if (!c->sc_ready) return fail(c, DRR_E_STATE, "drr_scatter: call drr_set_scatter_tables first");
-    if (c->vols.size() != 1 || !c->vols[0].dens) return fail(c, DRR_E_INVALID, "drr_scatter: exactly one volume is supported");
+    const int V = (int)c->vols.size();
+    if (V < 1) return fail(c, DRR_E_STATE, "drr_scatter: add a volume first");
+    for (int v = 0; v < V; v++)
+        if (!c->vols[v].dens) return fail(c, DRR_E_STATE, "drr_scatter: volume %d has no raw arrays", v);
     if (W <= 0 || H <= 0 || !w2i || !index_from_world || !source_world || !ijk_from_world || !out_tally)
         return fail(c, DRR_E_INVALID, "drr_scatter: bad arguments");
     CU(c, cudaSetDevice(c->device));
@@ -679,9 +685,15 @@ int drr_scatter(drr_ctx* c, unsigned long long n_photons, unsigned long long pho
     ScatterParams P;
     memset(&P, 0, sizeof P);
     P.T = c->sc;
-    const VolHost& h = c->vols[0];
-    P.vol.dens = h.dens; P.vol.lab = h.lab; P.vol.ni = h.ni; P.vol.nj = h.nj; P.vol.nk = h.nk;
-    memcpy(P.ijk, ijk_from_world, 48); memcpy(P.p_idx, index_from_world, 48); memcpy(P.w2i, w2i, 36); memcpy(P.src, source_world, 12);
+    P.V = V;
+    for (int v = 0; v < V; v++) {
+        const VolHost& h = c->vols[v];
+        P.vol[v].dens = h.dens; P.vol[v].lab = h.lab; P.vol[v].ni = h.ni; P.vol[v].nj = h.nj; P.vol[v].nk = h.nk;
+        P.priority[v] = c->priorities_set ? c->priority[v] : V - 1 - v;  // projector.py:489-492
+        P.enabled[v] = c->enabled[v];
+        memcpy(P.ijk[v], ijk_from_world + 12 * v, 48);
+    }
+    memcpy(P.p_idx, index_from_world, 48); memcpy(P.w2i, w2i, 36); memcpy(P.src, source_world, 12);
     P.W = W; P.H = H; P.n_bins = c->n_bins; P.spec_e_keV = c->d_energies; P.spec_cdf = c->d_sc_cdf;
     P.n_photons = n_photons; P.photon_offset = photon_offset; P.seed = seed;
     P.tally = c->d_sc_tally; P.counters = c->d_sc_counters;

@@ -7,7 +7,8 @@
 // published MC-GPU scheme (Badal & Badano, Med. Phys. 36, 2009) on those tables:
 //   * photon energy from the spectrum CDF, direction uniform over the detector area with the solid-angle
 //     weight cos^3(theta) carried as a statistical weight;
-//   * Woodcock (delta) tracking through the voxel volume with the per-energy minimum total mean free path;
+//   * Woodcock (delta) tracking through the voxel volumes (the one with the smallest priority value owns a point that lies in
+//     several, as in the ray march; between volumes is vacuum) with the per-energy minimum total mean free path;
 //   * interaction type by the ratio of inverse mean free paths; photoelectric absorption ends the history;
 //   * Rayleigh: angle from the RITA-sampled squared form factor (x^2 tables) with (1 + cos^2)/2 rejection;
 //   * Compton: relativistic impulse approximation with the analytical one-electron profiles of the shipped shell tables
@@ -35,8 +36,11 @@ struct ScatterTables {
 
 struct ScatterParams {
     ScatterTables T;
-    VolDev vol;
-    float ijk[12];               // ijk_from_world
+    int V;                       // volumes of the scene; a point inside several belongs to the one with the smallest priority value,
+    int priority[DRR_MAX_VOLUMES];  // as in the ray march (K.cu:458-496); outside all of them is vacuum
+    int enabled[DRR_MAX_VOLUMES];
+    VolDev vol[DRR_MAX_VOLUMES];
+    float ijk[DRR_MAX_VOLUMES][12];  // ijk_from_world per volume
     float p_idx[12];             // index_from_world (3x4): (u*w, v*w, w) = P (x, 1)
     float w2i[9];
     float src[3];
@@ -172,7 +176,26 @@ __device__ float sample_compton(const ScatterTables& T, int mat, float& E, curan
 __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ ScatterParams P) {
     const ScatterTables& T = P.T;
     double c_loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const float bx = (float)P.vol.ni - 0.5f, by = (float)P.vol.nj - 0.5f, bz = (float)P.vol.nk - 0.5f;
+    // [t0, t1] along (x, d) in which the photon can be inside some volume: union of the slab intervals of the volumes it hits
+    auto span = [&](float x, float y, float z, float dx, float dy, float dz, float& t0, float& t1) {
+        t0 = CUDART_INF_F; t1 = -CUDART_INF_F;
+        for (int v = 0; v < P.V; v++) {
+            if (!P.enabled[v]) continue;
+            const float* A = P.ijk[v];
+            const float d[3] = {A[0] * dx + A[1] * dy + A[2] * dz, A[4] * dx + A[5] * dy + A[6] * dz, A[8] * dx + A[9] * dy + A[10] * dz};
+            const float p[3] = {A[0] * x + A[1] * y + A[2] * z + A[3], A[4] * x + A[5] * y + A[6] * z + A[7], A[8] * x + A[9] * y + A[10] * z + A[11]};
+            const float mx[3] = {(float)P.vol[v].ni - 0.5f, (float)P.vol[v].nj - 0.5f, (float)P.vol[v].nk - 0.5f};
+            float a0 = 0.0f, a1 = CUDART_INF_F;
+            bool miss = false;
+            for (int a = 0; a < 3; a++) {
+                if (d[a] != 0.0f) {
+                    float ta = (-0.5f - p[a]) / d[a], tb = (mx[a] - p[a]) / d[a];
+                    a0 = fmaxf(a0, fminf(ta, tb)); a1 = fminf(a1, fmaxf(ta, tb));
+                } else if (p[a] < -0.5f || p[a] > mx[a]) miss = true;
+            }
+            if (!miss && a0 < a1) { t0 = fminf(t0, a0); t1 = fmaxf(t1, a1); }
+        }
+    };
     for (unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; id < P.n_photons;
          id += (unsigned long long)gridDim.x * blockDim.x) {
         curandStatePhilox4_32_10_t st;
@@ -190,23 +213,10 @@ __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ Sc
         float wgt = 1.0f / (rl * rl * rl);
         float x = P.src[0], y = P.src[1], z = P.src[2];
         c_loc[0] += (double)E * wgt;
-        // ---- to the volume ----------------------------------------------------------------------------
-        float di = P.ijk[0] * dx + P.ijk[1] * dy + P.ijk[2] * dz, dj = P.ijk[4] * dx + P.ijk[5] * dy + P.ijk[6] * dz,
-              dk = P.ijk[8] * dx + P.ijk[9] * dy + P.ijk[10] * dz;
-        float pi = P.ijk[0] * x + P.ijk[1] * y + P.ijk[2] * z + P.ijk[3], pj = P.ijk[4] * x + P.ijk[5] * y + P.ijk[6] * z + P.ijk[7],
-              pk = P.ijk[8] * x + P.ijk[9] * y + P.ijk[10] * z + P.ijk[11];
-        float t0 = 0.0f, t1 = CUDART_INF_F;
-        {
-            const float d[3] = {di, dj, dk}, p[3] = {pi, pj, pk}, mx[3] = {bx, by, bz};
-            bool miss = false;
-            for (int a = 0; a < 3; a++) {
-                if (d[a] != 0.0f) {
-                    float ta = (-0.5f - p[a]) / d[a], tb = (mx[a] - p[a]) / d[a];
-                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-                } else if (p[a] < -0.5f || p[a] > mx[a]) miss = true;
-            }
-            if (miss || t0 >= t1) { c_loc[1] += (double)E * wgt; continue; }
-        }
+        // ---- to the volumes ---------------------------------------------------------------------------
+        float t0, t1;
+        span(x, y, z, dx, dy, dz, t0, t1);
+        if (!(t0 < t1)) { c_loc[1] += (double)E * wgt; continue; }
         float t = t0 + 1e-4f;
         int n_scat = 0;
         bool alive = true;
@@ -218,20 +228,33 @@ __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ Sc
             float smax = T.majorant[ie] + wq * (T.majorant[ie + 1] - T.majorant[ie]);
             smax *= 1.0001f;
             t += -__logf(curand_uniform(&st)) / smax;
-            float qi = pi + t * di, qj = pj + t * dj, qk = pk + t * dk;
-            if (qi < -0.5f || qi > bx || qj < -0.5f || qj > by || qk < -0.5f || qk > bz) break;  // left the volume
-            int vi = min(max((int)floorf(qi + 0.5f), 0), P.vol.ni - 1), vj = min(max((int)floorf(qj + 0.5f), 0), P.vol.nj - 1),
-                vk = min(max((int)floorf(qk + 0.5f), 0), P.vol.nk - 1);
-            size_t o = ((size_t)vk * P.vol.nj + vj) * P.vol.ni + vi;
-            int mat = T.mat_of_label[__ldg(P.vol.lab + o)];
-            float rho = __ldg(P.vol.dens + o);
+            if (t > t1) break;  // behind the last volume
+            const float X = x + t * dx, Y = y + t * dy, Z = z + t * dz;
+            // the volume this point belongs to: smallest priority value among the volumes that contain it
+            int best = -1, best_pr = 0x7fffffff;
+            size_t o = 0;
+            for (int vv = 0; vv < P.V; vv++) {
+                if (!P.enabled[vv] || P.priority[vv] >= best_pr) continue;
+                const float* A = P.ijk[vv];
+                const float qi = A[0] * X + A[1] * Y + A[2] * Z + A[3], qj = A[4] * X + A[5] * Y + A[6] * Z + A[7],
+                            qk = A[8] * X + A[9] * Y + A[10] * Z + A[11];
+                const VolDev& vol = P.vol[vv];
+                if (qi < -0.5f || qi > (float)vol.ni - 0.5f || qj < -0.5f || qj > (float)vol.nj - 0.5f || qk < -0.5f || qk > (float)vol.nk - 0.5f) continue;
+                const int vi = min(max((int)floorf(qi + 0.5f), 0), vol.ni - 1), vj = min(max((int)floorf(qj + 0.5f), 0), vol.nj - 1),
+                          vk = min(max((int)floorf(qk + 0.5f), 0), vol.nk - 1);
+                best = vv; best_pr = P.priority[vv];
+                o = ((size_t)vk * vol.nj + vj) * vol.ni + vi;
+            }
+            if (best < 0) continue;  // between the volumes: vacuum, every interaction is virtual
+            int mat = T.mat_of_label[__ldg(P.vol[best].lab + o)];
+            float rho = __ldg(P.vol[best].dens + o);
             float iray, ico, itot, pmax;
             mfp_lookup(T, mat, E, iray, ico, itot, pmax);
             float scale = rho * T.inv_rho_nom[mat];
             if (curand_uniform(&st) * smax >= itot * scale) continue;  // virtual interaction
             float r = curand_uniform(&st) * itot;
             // move the photon to the interaction point
-            x += t * dx; y += t * dy; z += t * dz;
+            x = X; y = Y; z = Z;
             float cost;
             if (r < iray) { cost = sample_rayleigh(T, mat, E, pmax, &st); c_loc[6] += 1.0; }
             else if (r < iray + ico) { float E0 = E; cost = sample_compton(T, mat, E, &st); c_loc[2] += (double)(E0 - E) * wgt; c_loc[7] += 1.0; }
@@ -239,10 +262,7 @@ __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ Sc
             if (E < T.e0) { c_loc[2] += (double)E * wgt; alive = false; break; }
             rotate_dir(dx, dy, dz, cost, 6.283185307f * curand_uniform(&st));
             n_scat++;
-            di = P.ijk[0] * dx + P.ijk[1] * dy + P.ijk[2] * dz; dj = P.ijk[4] * dx + P.ijk[5] * dy + P.ijk[6] * dz;
-            dk = P.ijk[8] * dx + P.ijk[9] * dy + P.ijk[10] * dz;
-            pi = P.ijk[0] * x + P.ijk[1] * y + P.ijk[2] * z + P.ijk[3]; pj = P.ijk[4] * x + P.ijk[5] * y + P.ijk[6] * z + P.ijk[7];
-            pk = P.ijk[8] * x + P.ijk[9] * y + P.ijk[10] * z + P.ijk[11];
+            span(x, y, z, dx, dy, dz, t0, t1);
             t = 0.0f;
         }
         if (!alive) continue;

@@ -36,9 +36,9 @@ def load_tables():
 
 
 def setup(projector) -> None:
-    """Upload the interaction tables for ``projector``'s materials (one volume only)."""
-    if len(projector.volumes) != 1:
-        raise ValueError("scatter simulation supports exactly one volume")
+    """Upload the interaction tables for ``projector``'s materials (any number of volumes)."""
+    if len(projector.volumes) < 1:
+        raise ValueError("scatter simulation needs at least one volume")
     t = load_tables()
     names = [str(n) for n in t["names"]]
     mat_of_label = []
@@ -46,12 +46,16 @@ def setup(projector) -> None:
         if m not in MCGPU_NAME or MCGPU_NAME[m] not in names:
             raise ValueError(f"UNSUPPORTED MATERIAL FOR MCGPU: {m}")  # conv_to_mcgpu.py:24-33
         mat_of_label.append(names.index(MCGPU_NAME[m]))
-    vol = projector.volumes[0]
     from .scene import remap_labels
 
-    labels = remap_labels(vol, projector.all_materials)
-    rho_max = np.array([float(vol.data[labels == l].max()) if np.any(labels == l) else 0.0 for l in range(len(projector.all_materials))],
-                       dtype=np.float32)
+    rho_max = np.zeros(len(projector.all_materials), dtype=np.float32)   # largest density per material over all volumes: the majorant
+    for vol in projector.volumes:
+        labels = remap_labels(vol, projector.all_materials)
+        dens = np.asarray(vol.data)
+        for l in range(len(projector.all_materials)):
+            sel = labels == l
+            if np.any(sel):
+                rho_max[l] = max(rho_max[l], np.float32(dens[sel].max()))
     e = t["energy_eV"].astype(np.float64)
     mfp = np.ascontiguousarray(t["mfp_mm"], dtype=np.float32)
     rita = np.ascontiguousarray(t["rita"], dtype=np.float32)
@@ -78,6 +82,10 @@ def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int 
     p_idx = np.ascontiguousarray(np.asarray(proj.index_from_world, dtype=np.float64)[:3, :] / sdd, dtype=np.float32)
     src = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32)
     counters = np.zeros(8, dtype=np.float64)
+    V = len(projector.volumes)
+    pr = np.ascontiguousarray(projector.priorities, dtype=np.int32)
+    en = np.ascontiguousarray([1 if getattr(v, "enabled", True) else 0 for v in projector.volumes], dtype=np.int32)
+    _lib.check(_lib.load().drr_set_priorities(projector._h, _lib.ptr(pr), _lib.ptr(en), V), projector._h)
     if out is not None:
         if not (hasattr(out, "is_cuda") and out.is_cuda and out.is_contiguous() and out.numel() == W * H and out.element_size() == 8):
             raise ValueError("out must be a contiguous 64-bit integer CUDA tensor of H x W elements")
@@ -85,7 +93,7 @@ def simulate(projector, proj, n_photons: int, seed: int = 0, photon_offset: int 
     else:
         tally, mem = np.zeros((H, W), dtype=np.uint64), _lib.MEM_HOST
     _lib.check(_lib.load().drr_scatter(projector._h, int(n_photons), int(photon_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, W, H, _lib.ptr(w2i),
-                                       _lib.ptr(p_idx), _lib.ptr(src), _lib.ptr(np.ascontiguousarray(ijk[0])), _lib.ptr(tally), _lib.ptr(counters),
+                                       _lib.ptr(p_idx), _lib.ptr(src), _lib.ptr(np.ascontiguousarray(ijk)), _lib.ptr(tally), _lib.ptr(counters),
                                        mem), projector._h)
     return tally, counters
 

@@ -158,7 +158,9 @@ int drr_set_scatter_tables(drr_ctx* ctx, int n_mat, int n_e, float e0, float de,
 /* Simulates photons [photon_offset, photon_offset + n_photons) of the stream `seed` for one view and returns the
  * scatter tally: out_tally [H][W] uint64, energy x solid-angle weight in units of 2^-16 eV (exact integer sums, so
  * any split of the photon range over calls or GPUs adds up bit-identically; reduce across GPUs with ncclAllReduce).
- *   index_from_world: 3x4 K[R|t] divided by the source-to-detector distance (w == 1 on the detector plane).
+ *   index_from_world: 3x4 K[R|t] divided by the source-to-detector distance (w == 1 on the detector plane);
+ *   ijk_from_world [V][12]: one 3x4 per volume added (a point inside several volumes belongs to the one drr_set_priorities
+ *   ranks first, as in the ray march; space between the volumes is vacuum).
  *   out_counters (host, may be NULL): energy bookkeeping, eV x weight: emitted, missed the volume, absorbed, left
  *   unscattered, scattered & detected, scattered & missed the detector; then #Rayleigh and #Compton events. */
 int drr_scatter(drr_ctx* ctx, unsigned long long n_photons, unsigned long long photon_offset, uint64_t seed, int W, int H,

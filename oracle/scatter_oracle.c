@@ -29,10 +29,13 @@ typedef struct {
     const float* inv_rho_nom;  /* [n_mat] */
     const float* majorant;     /* [n_e] */
     const int* mat_of_label;   /* [M] */
-    const float* dens;         /* [ni][nj][nk] g/cm^3 (NumPy order of Volume.data) */
-    const uint8_t* lab;        /* [ni][nj][nk] global material index */
-    int ni, nj, nk;
-    float ijk[12], p_idx[12], w2i[9], src[3];
+    int V;                     /* volumes; a point inside several belongs to the one with the smallest priority value */
+    int priority[8], enabled[8];
+    const float* dens[8];      /* [ni][nj][nk] g/cm^3 (NumPy order of Volume.data) */
+    const uint8_t* lab[8];     /* [ni][nj][nk] global material index */
+    int shape[8][3];
+    float ijk[8][12];          /* ijk_from_world per volume */
+    float p_idx[12], w2i[9], src[3];
     int W, H, n_bins;
     const float* spec_e_keV;
     const float* spec_cdf;
@@ -186,10 +189,29 @@ static float sample_compton(const sc_scene* S, int mat, float* Eio, philox* st) 
     return fmaxf(-1.0f, fminf(1.0f, cdt));
 }
 
+/* [t0, t1] along (x, d) in which the photon can be inside some volume: union of the slab intervals of the volumes it hits */
+static void span(const sc_scene* S, float x, float y, float z, float dx, float dy, float dz, float* t0, float* t1) {
+    *t0 = INFINITY; *t1 = -INFINITY;
+    for (int v = 0; v < S->V; v++) {
+        if (!S->enabled[v]) continue;
+        const float* A = S->ijk[v];
+        const float d[3] = {A[0] * dx + A[1] * dy + A[2] * dz, A[4] * dx + A[5] * dy + A[6] * dz, A[8] * dx + A[9] * dy + A[10] * dz};
+        const float p[3] = {A[0] * x + A[1] * y + A[2] * z + A[3], A[4] * x + A[5] * y + A[6] * z + A[7], A[8] * x + A[9] * y + A[10] * z + A[11]};
+        const float mx[3] = {(float)S->shape[v][0] - 0.5f, (float)S->shape[v][1] - 0.5f, (float)S->shape[v][2] - 0.5f};
+        float a0 = 0.0f, a1 = INFINITY;
+        int miss = 0;
+        for (int a = 0; a < 3; a++) {
+            if (d[a] != 0.0f) {
+                float ta = (-0.5f - p[a]) / d[a], tb = (mx[a] - p[a]) / d[a];
+                a0 = fmaxf(a0, fminf(ta, tb)); a1 = fminf(a1, fmaxf(ta, tb));
+            } else if (p[a] < -0.5f || p[a] > mx[a]) miss = 1;
+        }
+        if (!miss && a0 < a1) { *t0 = fminf(*t0, a0); *t1 = fmaxf(*t1, a1); }
+    }
+}
+
 /* Photon ids [offset, offset + n): tally[H*W] in 2^-16 eV fixed point, counters[8] as in csrc/drr_scatter.cu. */
 int drr_scatter_oracle(const sc_scene* S, uint64_t n_photons, uint64_t offset, uint64_t seed, uint64_t* tally, double* counters) {
-    const float bx = (float)S->ni - 0.5f, by = (float)S->nj - 0.5f, bz = (float)S->nk - 0.5f;
-    const float* A = S->ijk;
     for (uint64_t id = 0; id < n_photons; id++) {
         philox st;
         philox_init(&st, seed, offset + id);
@@ -206,20 +228,9 @@ int drr_scatter_oracle(const sc_scene* S, uint64_t n_photons, uint64_t offset, u
         float wgt = 1.0f / (rl * rl * rl);
         float x = S->src[0], y = S->src[1], z = S->src[2];
         counters[0] += (double)E * wgt;
-        float di = A[0] * dx + A[1] * dy + A[2] * dz, dj = A[4] * dx + A[5] * dy + A[6] * dz, dk = A[8] * dx + A[9] * dy + A[10] * dz;
-        float pi = A[0] * x + A[1] * y + A[2] * z + A[3], pj = A[4] * x + A[5] * y + A[6] * z + A[7], pk = A[8] * x + A[9] * y + A[10] * z + A[11];
-        float t0 = 0.0f, t1 = INFINITY;
-        {
-            const float d[3] = {di, dj, dk}, p[3] = {pi, pj, pk}, mx[3] = {bx, by, bz};
-            int miss = 0;
-            for (int a = 0; a < 3; a++) {
-                if (d[a] != 0.0f) {
-                    float ta = (-0.5f - p[a]) / d[a], tb = (mx[a] - p[a]) / d[a];
-                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-                } else if (p[a] < -0.5f || p[a] > mx[a]) miss = 1;
-            }
-            if (miss || t0 >= t1) { counters[1] += (double)E * wgt; continue; }
-        }
+        float t0, t1;
+        span(S, x, y, z, dx, dy, dz, &t0, &t1);
+        if (!(t0 < t1)) { counters[1] += (double)E * wgt; continue; }
         float t = t0 + 1e-4f;
         int n_scat = 0, alive = 1;
         /* Woodcock tracking with the per-energy majorant */
@@ -232,21 +243,32 @@ int drr_scatter_oracle(const sc_scene* S, uint64_t n_photons, uint64_t offset, u
             float smax = S->majorant[ie] + wq * (S->majorant[ie + 1] - S->majorant[ie]);
             smax *= 1.0001f;
             t += -logf(philox_uniform(&st)) / smax;
-            float qi = pi + t * di, qj = pj + t * dj, qk = pk + t * dk;
-            if (qi < -0.5f || qi > bx || qj < -0.5f || qj > by || qk < -0.5f || qk > bz) break;
-            int vi = (int)floorf(qi + 0.5f), vj = (int)floorf(qj + 0.5f), vk = (int)floorf(qk + 0.5f);
-            vi = vi < 0 ? 0 : (vi > S->ni - 1 ? S->ni - 1 : vi);
-            vj = vj < 0 ? 0 : (vj > S->nj - 1 ? S->nj - 1 : vj);
-            vk = vk < 0 ? 0 : (vk > S->nk - 1 ? S->nk - 1 : vk);
-            size_t o = ((size_t)vi * S->nj + vj) * S->nk + vk;
-            int mat = S->mat_of_label[S->lab[o]];
-            float rho = S->dens[o];
+            if (t > t1) break;
+            const float X = x + t * dx, Y = y + t * dy, Z = z + t * dz;
+            int best = -1, best_pr = 0x7fffffff;
+            size_t o = 0;
+            for (int vv = 0; vv < S->V; vv++) {
+                if (!S->enabled[vv] || S->priority[vv] >= best_pr) continue;
+                const float* A = S->ijk[vv];
+                const float qi = A[0] * X + A[1] * Y + A[2] * Z + A[3], qj = A[4] * X + A[5] * Y + A[6] * Z + A[7], qk = A[8] * X + A[9] * Y + A[10] * Z + A[11];
+                const int ni = S->shape[vv][0], nj = S->shape[vv][1], nk = S->shape[vv][2];
+                if (qi < -0.5f || qi > (float)ni - 0.5f || qj < -0.5f || qj > (float)nj - 0.5f || qk < -0.5f || qk > (float)nk - 0.5f) continue;
+                int vi = (int)floorf(qi + 0.5f), vj = (int)floorf(qj + 0.5f), vk = (int)floorf(qk + 0.5f);
+                vi = vi < 0 ? 0 : (vi > ni - 1 ? ni - 1 : vi);
+                vj = vj < 0 ? 0 : (vj > nj - 1 ? nj - 1 : vj);
+                vk = vk < 0 ? 0 : (vk > nk - 1 ? nk - 1 : vk);
+                best = vv; best_pr = S->priority[vv];
+                o = ((size_t)vi * nj + vj) * nk + vk;
+            }
+            if (best < 0) continue;  /* vacuum between the volumes */
+            int mat = S->mat_of_label[S->lab[best][o]];
+            float rho = S->dens[best][o];
             float iray, ico, itot, pmax;
             mfp_lookup(S, mat, E, &iray, &ico, &itot, &pmax);
             float scale = rho * S->inv_rho_nom[mat];
             if (philox_uniform(&st) * smax >= itot * scale) continue;  /* virtual interaction */
             float r = philox_uniform(&st) * itot;
-            x += t * dx; y += t * dy; z += t * dz;
+            x = X; y = Y; z = Z;
             float cost;
             if (r < iray) { cost = sample_rayleigh(S, mat, E, pmax, &st); counters[6] += 1.0; }
             else if (r < iray + ico) { float E0 = E; cost = sample_compton(S, mat, &E, &st); counters[2] += (double)(E0 - E) * wgt; counters[7] += 1.0; }
@@ -254,8 +276,7 @@ int drr_scatter_oracle(const sc_scene* S, uint64_t n_photons, uint64_t offset, u
             if (E < S->e0) { counters[2] += (double)E * wgt; alive = 0; break; }
             rotate_dir(&dx, &dy, &dz, cost, 6.283185307f * philox_uniform(&st));
             n_scat++;
-            di = A[0] * dx + A[1] * dy + A[2] * dz; dj = A[4] * dx + A[5] * dy + A[6] * dz; dk = A[8] * dx + A[9] * dy + A[10] * dz;
-            pi = A[0] * x + A[1] * y + A[2] * z + A[3]; pj = A[4] * x + A[5] * y + A[6] * z + A[7]; pk = A[8] * x + A[9] * y + A[10] * z + A[11];
+            span(S, x, y, z, dx, dy, dz, &t0, &t1);
             t = 0.0f;
         }
         if (!alive) continue;
@@ -268,9 +289,9 @@ int drr_scatter_oracle(const sc_scene* S, uint64_t n_photons, uint64_t offset, u
         if (wd > 1e-9f) {
             float s = (1.0f - w0) / wd;
             if (s > 0.0f) {
-                float X = x + s * dx, Y = y + s * dy, Z = z + s * dz;
-                float uu = P[0] * X + P[1] * Y + P[2] * Z + P[3];
-                float vv = P[4] * X + P[5] * Y + P[6] * Z + P[7];
+                float Xd = x + s * dx, Yd = y + s * dy, Zd = z + s * dz;
+                float uu = P[0] * Xd + P[1] * Yd + P[2] * Zd + P[3];
+                float vv = P[4] * Xd + P[5] * Yd + P[6] * Zd + P[7];
                 int iu = (int)floorf(uu), iv = (int)floorf(vv);
                 if (iu >= 0 && iu < S->W && iv >= 0 && iv < S->H) {
                     hit = 1;

@@ -21,8 +21,9 @@ class _Scene(ctypes.Structure):
     _fields_ = [("n_mat", ctypes.c_int), ("n_e", ctypes.c_int), ("e0", ctypes.c_float), ("de", ctypes.c_float),
                 ("mfp", ctypes.c_void_p), ("rita", ctypes.c_void_p), ("compton", ctypes.c_void_p), ("nshell", ctypes.c_void_p),
                 ("inv_rho_nom", ctypes.c_void_p), ("majorant", ctypes.c_void_p), ("mat_of_label", ctypes.c_void_p),
-                ("dens", ctypes.c_void_p), ("lab", ctypes.c_void_p), ("ni", ctypes.c_int), ("nj", ctypes.c_int), ("nk", ctypes.c_int),
-                ("ijk", ctypes.c_float * 12), ("p_idx", ctypes.c_float * 12), ("w2i", ctypes.c_float * 9), ("src", ctypes.c_float * 3),
+                ("V", ctypes.c_int), ("priority", ctypes.c_int * 8), ("enabled", ctypes.c_int * 8),
+                ("dens", ctypes.c_void_p * 8), ("lab", ctypes.c_void_p * 8), ("shape", (ctypes.c_int * 3) * 8),
+                ("ijk", (ctypes.c_float * 12) * 8), ("p_idx", ctypes.c_float * 12), ("w2i", ctypes.c_float * 9), ("src", ctypes.c_float * 3),
                 ("W", ctypes.c_int), ("H", ctypes.c_int), ("n_bins", ctypes.c_int), ("spec_e_keV", ctypes.c_void_p), ("spec_cdf", ctypes.c_void_p)]
 
 
@@ -63,18 +64,26 @@ def compton_samples(material: str, energy_eV: float, n: int, seed: int = 0):
     return cost, e_out
 
 
-def simulate(volume, all_materials, spectrum_energies_keV, spectrum_pdf, proj, sdd: float, n_photons: int, seed: int = 0, photon_offset: int = 0):
-    """Same contract as ``deepdrr_b200.scatter.simulate``: (tally uint64 [H, W], counters float64 [8])."""
+def simulate(volumes, all_materials, spectrum_energies_keV, spectrum_pdf, proj, sdd: float, n_photons: int, seed: int = 0, photon_offset: int = 0,
+             priorities=None):
+    """Same contract as ``deepdrr_b200.scatter.simulate``: (tally uint64 [H, W], counters float64 [8]).  ``volumes``: one Volume or a list."""
     from deepdrr_b200 import geo
     from deepdrr_b200.scatter import MCGPU_NAME, load_tables
-    from deepdrr_b200.scene import remap_labels
+    from deepdrr_b200.scene import default_priorities, remap_labels
 
+    volumes = list(volumes) if isinstance(volumes, (list, tuple)) else [volumes]
+    V = len(volumes)
+    priorities = list(priorities) if priorities is not None else default_priorities(V)
     t = load_tables()
     names = [str(n) for n in t["names"]]
     mol = np.ascontiguousarray([names.index(MCGPU_NAME[m]) for m in all_materials], dtype=np.int32)
-    labels = np.ascontiguousarray(remap_labels(volume, all_materials))
-    dens = np.ascontiguousarray(volume.data, dtype=np.float32)
-    rho_max = np.array([float(dens[labels == l].max()) if np.any(labels == l) else 0.0 for l in range(len(all_materials))], dtype=np.float32)
+    labels = [np.ascontiguousarray(remap_labels(v, all_materials)) for v in volumes]
+    dens = [np.ascontiguousarray(v.data, dtype=np.float32) for v in volumes]
+    rho_max = np.zeros(len(all_materials), dtype=np.float32)
+    for d, lab in zip(dens, labels):
+        for l in range(len(all_materials)):
+            if np.any(lab == l):
+                rho_max[l] = max(rho_max[l], np.float32(d[lab == l].max()))
     e = t["energy_eV"].astype(np.float64)
     mfp = np.ascontiguousarray(t["mfp_mm"], dtype=np.float32)
     rita = np.ascontiguousarray(t["rita"], dtype=np.float32)
@@ -93,7 +102,7 @@ def simulate(volume, all_materials, spectrum_energies_keV, spectrum_pdf, proj, s
     cdf[-1] = 1.0
     ekev = np.ascontiguousarray(spectrum_energies_keV, dtype=np.float32)
     W, H = proj.intrinsic.sensor_size
-    w2i, _, ijk = geo.pose_arrays(proj, [volume])
+    w2i, _, ijk = geo.pose_arrays(proj, volumes)
     p_idx = np.ascontiguousarray(np.asarray(proj.index_from_world, dtype=np.float64)[:3, :] / float(sdd), dtype=np.float32).reshape(12)
     src = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32)
     S = _Scene()
@@ -101,9 +110,12 @@ def simulate(volume, all_materials, spectrum_energies_keV, spectrum_pdf, proj, s
     keep = [mfp, rita, comp, nshell, inv_rho, maj, mol, dens, labels, ekev, cdf]
     S.mfp, S.rita, S.compton, S.nshell = mfp.ctypes.data, rita.ctypes.data, comp.ctypes.data, nshell.ctypes.data
     S.inv_rho_nom, S.majorant, S.mat_of_label = inv_rho.ctypes.data, maj.ctypes.data, mol.ctypes.data
-    S.dens, S.lab = dens.ctypes.data, labels.ctypes.data
-    S.ni, S.nj, S.nk = dens.shape
-    S.ijk[:] = [float(x) for x in ijk[0]]
+    S.V = V
+    for v in range(V):
+        S.priority[v], S.enabled[v] = int(priorities[v]), int(bool(getattr(volumes[v], "enabled", True)))
+        S.dens[v], S.lab[v] = dens[v].ctypes.data, labels[v].ctypes.data
+        S.shape[v][:] = [int(x) for x in dens[v].shape]
+        S.ijk[v][:] = [float(x) for x in ijk[v]]
     S.p_idx[:] = [float(x) for x in p_idx]
     S.w2i[:] = [float(x) for x in w2i]
     S.src[:] = [float(x) for x in src]

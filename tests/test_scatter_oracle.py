@@ -115,3 +115,63 @@ def test_cuda_kernel_matches_the_restatement_on_the_same_photon_streams():
     mean_dep = c_tally.sum() / hits
     sigma = np.sqrt(2.0 * np.maximum(C, mean_dep) * mean_dep)
     assert np.all(np.abs(G - C) <= 3.0 * sigma), float((np.abs(G - C) / sigma).max())
+
+
+def _two_slabs():
+    """Two 64 x 64 slabs of soft tissue, 40 mm thick each, 60 mm of vacuum between them, plus a bone plate that overlaps the lower
+    slab and outranks it (priority 0 < 1): the union a multi-volume scene has to track through."""
+    lower, upper = _slab(40.0), _slab(40.0)
+    lower.translate((0.0, 0.0, -50.0))
+    upper.translate((0.0, 0.0, 50.0))
+    n = 24
+    data = np.full((n, n, 6), 1.9, dtype=np.float32)
+    a = np.diag([4.0, 4.0, 2.0, 1.0])
+    a[:3, 3] = [-4.0 * (n - 1) / 2, -4.0 * (n - 1) / 2, -5.0]
+    plate = Volume(data, ({"bone": 0}, np.zeros(data.shape, np.uint16)), anatomical_from_IJK=geo.FrameTransform(a))
+    plate.translate((0.0, 0.0, -50.0))
+    return [lower, upper, plate], [1, 1, 0]
+
+
+def test_restatement_tracks_through_several_volumes():
+    """Unscattered fraction through two separated slabs = exp(-(L1 + L2) / mfp): the vacuum between them attenuates nothing, and a
+    scene split into two volumes behaves like the same matter in one."""
+    lower, upper = _slab(40.0), _slab(40.0)
+    lower.translate((0.0, 0.0, -50.0))
+    upper.translate((0.0, 0.0, 50.0))
+    carm = phantoms.MobileCArmGeometry(sensor_width=64, sensor_height=64, pixel_size=0.5)
+    pose = carm.camera_projection(0.0, 0.0, (0, 0, 0))
+    e, pdf = spectrum_tables(get_spectrum(_mono(60.0)))
+    N = 150_000
+    _, c = scatter_oracle.simulate([lower, upper], ["soft tissue"], e, pdf, pose, carm.source_to_detector_distance, N, seed=2)
+    t = scatter.load_tables()
+    m = [str(x) for x in t["names"]].index("soft tissue")
+    ie = int(round((60000.0 - t["energy_eV"][0]) / (t["energy_eV"][1] - t["energy_eV"][0])))
+    mfp_tot = float(t["mfp_mm"][m, ie, 3])
+    expect = np.exp(-80.0 / mfp_tot)
+    assert abs(c[3] / c[0] - expect) < 4 * np.sqrt(expect * (1 - expect) / N) + 3e-4 * expect
+    assert abs(c[0] - c[1:6].sum()) <= 1e-9 * c[0]
+
+
+@pytest.mark.gpu
+def test_cuda_multi_volume_scatter_matches_the_restatement():
+    volumes, priorities = _two_slabs()
+    carm = phantoms.MobileCArmGeometry(sensor_width=96, sensor_height=64, pixel_size=3.0)
+    pose = carm.camera_projection(0.15, -0.1, (5.0, 0.0, 0.0))
+    N = 100_000
+    with Projector(volumes, priorities=priorities, device=_Dev(carm, pose), spectrum="90KV_AL40", neglog=False, scatter_num=N) as p:
+        mats = p.all_materials
+        g_tally, g_c = scatter.simulate(p, pose, N, seed=9)
+        img = p.project()                                               # primary + scatter through the public call
+        p.scatter_num = 0
+        primary = p.project()
+    e, pdf = spectrum_tables(get_spectrum("90KV_AL40"))
+    c_tally, c_c = scatter_oracle.simulate(volumes, mats, e, pdf, pose, carm.source_to_detector_distance, N, seed=9, priorities=priorities)
+    assert abs(g_c[0] - c_c[0]) <= 1e-6 * c_c[0]
+    for k in (2, 3, 4, 5, 6, 7):
+        assert abs(g_c[k] - c_c[k]) <= 0.006 * c_c[k], (k, g_c[k], c_c[k])
+    assert float(np.mean(g_tally == c_tally)) > 0.85
+    assert np.all(img >= primary) and float((img - primary).sum()) > 0
+    # the bone plate outranks the slab it sits in: more photoabsorption than the same scene without it
+    with Projector(volumes[:2], device=_Dev(carm, pose), spectrum="90KV_AL40", neglog=False, scatter_num=N) as p:
+        _, c2 = scatter.simulate(p, pose, N, seed=9)
+    assert g_c[2] > 1.02 * c2[2]
