@@ -23,7 +23,7 @@ cudaError_t drr_launch_spectral(const float* area, int n_bins, int M, const floa
 cudaError_t drr_launch_noise(float* intensity, const float* pprob, float* scratch, int W, int H, int n_views, float photon_count,
                              unsigned long long seed, cudaStream_t s);
 cudaError_t drr_launch_clip(float* img, size_t total, float upper, cudaStream_t s);
-cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* minmax, float epsilon, cudaStream_t s);
+cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* minmax, float epsilon, cudaStream_t s, int* const_flag = nullptr);
 cudaError_t drr_launch_collected(float* intensity, float* solid, double* view_sum, const ViewDev* views, int W, int H, int n_views,
                                  float photon_count, float pixel_area, cudaStream_t s);
 
@@ -183,7 +183,11 @@ struct VolHost {
 struct drr_ctx {
     int device = 0;
     int n_sm = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t evp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // copy / compute pipeline of drr_project
+    int* d_const_flag = nullptr;
+    int h_const_flag = 0;
+    int pipeline = 1;  // DRR_TUNE_PIPELINE: host-bound batches are projected in two halves, the copy of one under the march of the other
     std::string err;
     // spectrum
     int n_bins = 0, M = 0;
@@ -302,7 +306,10 @@ int drr_create(int device_id, drr_ctx** out) {
     c->n_sm = prop.multiProcessorCount;
     CU(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CU(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 5; i++) CU(nullptr, cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 7; i++) CU(nullptr, cudaEventCreate(&c->evp[i]));
+    CU(nullptr, cudaMalloc(&c->d_const_flag, sizeof(int)));
     CU(nullptr, cudaMalloc(&c->d_samples, 2 * sizeof(unsigned long long)));  // [0] march steps, [1] steps inside a volume window
     CU(nullptr, cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
     for (int i = 0; i < DRR_MAX_VOLUMES; i++) { c->priority[i] = 0; c->enabled[i] = 1; }
@@ -337,6 +344,9 @@ int drr_destroy(drr_ctx* c) {
     cudaFree(c->d_area); cudaFree(c->d_intensity); cudaFree(c->d_pprob); cudaFree(c->d_scratch);
     cudaFree(c->d_minmax); cudaFree(c->d_viewsum); cudaFree(c->d_samples); cudaFree(c->d_tile_counter);
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 7; i++) if (c->evp[i]) cudaEventDestroy(c->evp[i]);
+    cudaFree(c->d_const_flag);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return DRR_OK;
@@ -521,6 +531,7 @@ int drr_set_tuning(drr_ctx* c, int key, int value) {  // tuning knobs (results d
     if (!c) return DRR_E_INVALID;
     if (key == DRR_TUNE_TEX_EIGHTHS && value >= 0 && value <= 8) { c->tex_eighths = value; return DRR_OK; }
     if (key == DRR_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) { c->variant = value; return DRR_OK; }
+    if (key == DRR_TUNE_PIPELINE && (value == 0 || value == 1)) { c->pipeline = value; return DRR_OK; }
     return fail(c, DRR_E_INVALID, "drr_set_tuning: bad key/value %d/%d", key, value);
 }
 
@@ -983,12 +994,58 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         P.tex_eighths = sampler == DRR_SAMPLER_ALU ? 0 : (sampler == DRR_SAMPLER_TEX ? 8 : c->tex_eighths);
     }
     const bool lockstep_ok = V > 0 && march_slack(c, n_views, src_ijk, ijk_from_world, max_ray_length, P);
+    // ---- host-bound single-volume batches: two halves, the device-to-host copy of the first under the march of the second -----
+    // (projector.py:786-792 copies every view back before the next one starts; here only the second half's copy is exposed)
+    const bool lockstep_single = single && h_has_cells(c) && (c->variant == 0 ? lockstep_ok : true) &&
+                                 pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0;
+    if (lockstep_single && c->pipeline && out_intensity && !out_area && !out_pprob && out_mem_kind == DRR_MEM_HOST && n_views >= 4 &&
+        !(post_flags & (DRR_POST_NOISE | DRR_POST_COLLECTED))) {
+        if (c->minmax_cap < n_views) {
+            cudaFree(c->d_minmax); cudaFree(c->d_viewsum);
+            CU(c, cudaMalloc(&c->d_minmax, sizeof(unsigned) * 2 * n_views));
+            CU(c, cudaMalloc(&c->d_viewsum, sizeof(double) * n_views));
+            c->minmax_cap = n_views;
+        }
+        CU(c, cudaMemsetAsync(c->d_const_flag, 0, sizeof(int), s));
+        const int first = n_views / 2;
+        for (int k = 0; k < 2; k++) {
+            const int v0 = k ? first : 0, nv = k ? n_views - first : first;
+            MarchParams Pk = P;
+            Pk.views = c->d_views + v0; Pk.area = c->d_area + (size_t)v0 * M * npix; Pk.n_views = nv;
+            if (k) CU(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), s));
+            CU(c, cudaEventRecord(c->evp[3 * k], s));
+            CU(c, drr_launch_march_warp(Pk, c->n_sm, s));
+            CU(c, cudaEventRecord(c->evp[3 * k + 1], s));
+            float* img = c->d_intensity + (size_t)v0 * npix;
+            CU(c, drr_launch_spectral(Pk.area, c->n_bins, M, c->d_energies, c->d_pdf, c->d_mu, npix, nv, img, c->d_pprob + (size_t)v0 * npix, c->n_sm, s));
+            c->launches += 2;
+            if (post_flags & DRR_POST_CLIP) { CU(c, drr_launch_clip(img, npix * nv, intensity_upper_bound, s)); c->launches += 1; }
+            if (post_flags & DRR_POST_NEGLOG) { CU(c, drr_launch_neglog(img, npix, nv, c->d_minmax + 2 * v0, 0.01f, s, c->d_const_flag)); c->launches += 2; }
+            CU(c, cudaEventRecord(c->evp[3 * k + 2], s));
+            CU(c, cudaStreamWaitEvent(c->copy_stream, c->evp[3 * k + 2], 0));
+            CU(c, cudaMemcpyAsync(out_intensity + (size_t)v0 * npix, img, sizeof(float) * npix * nv, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        CU(c, cudaEventRecord(c->evp[6], c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->last_samples, c->d_samples, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(c, cudaMemcpyAsync(&c->h_const_flag, c->d_const_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(c, cudaStreamSynchronize(s));
+        CU(c, cudaStreamSynchronize(c->copy_stream));
+        // utils.neglog zeroes the WHOLE batch when any image of it is constant (image_utils.py:42-49): a piece that met one has
+        // zeroed itself; tell the other piece
+        if ((post_flags & DRR_POST_NEGLOG) && c->h_const_flag) memset(out_intensity, 0, sizeof(float) * npix * n_views);
+        float m0 = 0, m1 = 0, p0 = 0, p1 = 0, tot = 0;
+        CU(c, cudaEventElapsedTime(&m0, c->evp[0], c->evp[1])); CU(c, cudaEventElapsedTime(&m1, c->evp[3], c->evp[4]));
+        CU(c, cudaEventElapsedTime(&p0, c->evp[1], c->evp[2])); CU(c, cudaEventElapsedTime(&p1, c->evp[4], c->evp[5]));
+        CU(c, cudaEventElapsedTime(&tot, c->ev[0], c->evp[6]));
+        c->last_ms[0] = m0 + m1; c->last_ms[1] = p0 + p1; c->last_ms[2] = tot;
+        return DRR_OK;
+    }
     CU(c, cudaEventRecord(c->ev[1], s));
     if (V == 0) {
         if (meshes) { CU(c, drr_launch_march_meshonly(P, s)); c->launches += 1; }
         else CU(c, cudaMemsetAsync(c->d_area, 0, sizeof(float) * npix * M * n_views, s));
     } else if (single) {
-        if (h_has_cells(c) && (c->variant == 0 ? lockstep_ok : true) && pick_variant(c, w2i, src_ijk, ijk_from_world, W, H) == 0) {
+        if (lockstep_single) {
             CU(c, drr_launch_march_warp(P, c->n_sm, s));  // persistent: every warp pulls 8x4-pixel tiles from the queue
         } else {
             int occ = drr_march_single_occupancy(M);

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ i
 }
 
 __global__ void __launch_bounds__(256) neglog_kernel(float* __restrict__ img, size_t npix, int n_views,
-                                                     const unsigned* __restrict__ minmax, float epsilon) {
+                                                     const unsigned* __restrict__ minmax, float epsilon, int* __restrict__ const_flag) {
     // "if np.any(image_max == image_min): image[:] = 0" zeroes the whole batch (image_utils.py:42-49)
     __shared__ int s_const;
     if (threadIdx.x == 0) s_const = 0;
@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256) neglog_kernel(float* __restrict__ img, si
     }
     __syncthreads();
     const bool all_zero = s_const != 0;
+    // a batch projected in pieces (drr_project's copy / compute pipeline) learns here that one piece held a constant image
+    if (all_zero && const_flag != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *const_flag = 1;
     const int view = blockIdx.y;
     const float mn = key2f(minmax[2 * view]), mx = key2f(minmax[2 * view + 1]);
     const float shift = __fadd_rn(mn, epsilon);
@@ -252,7 +254,7 @@ cudaError_t drr_launch_clip(float* img, size_t total, float upper, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* minmax, float epsilon, cudaStream_t s) {
+cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* minmax, float epsilon, cudaStream_t s, int* const_flag) {
     // minmax initial values: (0xFFFFFFFF, 0) per view
     cudaError_t e = cudaMemsetAsync(minmax, 0, sizeof(unsigned) * 2 * n_views, s);
     if (e != cudaSuccess) return e;
@@ -263,7 +265,7 @@ cudaError_t drr_launch_neglog(float* img, size_t npix, int n_views, unsigned* mi
     if (gx < 1) gx = 1;
     dim3 grid(gx, n_views);
     minmax_kernel<<<grid, 256, 0, s>>>(img, npix, minmax);
-    neglog_kernel<<<grid, 256, 0, s>>>(img, npix, n_views, minmax, epsilon);
+    neglog_kernel<<<grid, 256, 0, s>>>(img, npix, n_views, minmax, epsilon, const_flag);
     return cudaGetLastError();
 }
 

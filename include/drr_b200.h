@@ -93,12 +93,15 @@ int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int ai
 
 /* Tuning knobs; results stay within the parity tolerance whatever they are set to.
  *   DRR_TUNE_TEX_EIGHTHS    DRR_SAMPLER_HYBRID: how many of every 8 consecutive steps of a uniform segment fetch
- *                           density through the texture unit (the rest emulate it on the FMA pipes); 0, 4 (default),
- *                           5, 6, 7 or 8 (1..3 run as 4).
+ *                           density through the texture unit (the rest emulate it on the FMA pipes); 0, 3, 4 (default),
+ *                           5 or 8 (1..2 run as 3, 6..7 as 5).
  *   DRR_TUNE_KERNEL_VARIANT single-volume march: 0 = warp-cooperative shared-memory staging (default),
- *                           1 = per-ray register cell cache. */
+ *                           1 = per-ray register cell cache.
+ *   DRR_TUNE_PIPELINE       1 (default): a batch of >= 4 views bound for host memory is projected in two halves, the
+ *                           device-to-host copy of the first under the march of the second; 0: one piece. */
 #define DRR_TUNE_TEX_EIGHTHS 0
 #define DRR_TUNE_KERNEL_VARIANT 1
+#define DRR_TUNE_PIPELINE 2
 int drr_set_tuning(drr_ctx* ctx, int key, int value);
 
 /* Mesh inputs of projectKernel (project_kernel.cu:172-177, 363-375, 498-517, 569-579), per view,

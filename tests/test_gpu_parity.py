@@ -463,3 +463,29 @@ def test_gpu_side_hu_preparation_is_bit_identical_to_the_host_path():
             out.append(p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length))
     assert dev_._host is None
     assert np.array_equal(out[0], out[1])
+
+
+def test_pipelined_host_batches_equal_single_piece_batches():
+    """drr_project projects a host-bound batch of >= 4 views in two halves so that the copy of the first runs under the march of
+    the second.  Same bits as in one piece -- including utils.neglog's quirk that ONE constant image zeroes the WHOLE batch
+    (utils/image_utils.py:42-49), whichever half it is in."""
+    vol_ = phantoms.thorax_volume((64, 64, 50), (6.4, 6.4, 8.0), seed=7)
+    carm = phantoms.MobileCArmGeometry(sensor_width=96, sensor_height=80, pixel_size=3.1)
+    poses = phantoms.c2_poses(7, seed=31, carm=carm)
+    away = phantoms.look_at_projection((0.0, 0.0, 5000.0), (0.0, 0.0, 1.0), (0, 1, 0), carm.camera_intrinsics)   # sees nothing: constant image
+    with Projector(vol_, spectrum="120KV_AL43", neglog=True, camera_intrinsics=carm.camera_intrinsics) as p:
+        for batch in (poses, poses[:4], poses[:3] + [away] + poses[3:6], [away] + poses[:5], poses[:5] + [away]):
+            p.set_pipeline(True)
+            a = p.project(*batch, max_ray_length=carm.max_ray_length).copy()
+            p.set_pipeline(False)
+            b = p.project(*batch, max_ray_length=carm.max_ray_length).copy()
+            assert np.array_equal(a, b)
+            if any(q is away for q in batch):
+                assert not a.any()
+            else:
+                assert a.min() == 0.0 and a.max() == 1.0
+        p.neglog = False
+        p.set_pipeline(True)
+        raw = p.project(*poses, max_ray_length=carm.max_ray_length).copy()
+        p.set_pipeline(False)
+        assert np.array_equal(raw, p.project(*poses, max_ray_length=carm.max_ray_length))
