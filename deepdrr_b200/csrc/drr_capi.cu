@@ -187,7 +187,8 @@ struct drr_ctx {
     cudaEvent_t evp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // copy / compute pipeline of drr_project
     int* d_const_flag = nullptr;
     int h_const_flag = 0;
-    int pipeline = 1;  // DRR_TUNE_PIPELINE: host-bound batches are projected in two halves, the copy of one under the march of the other
+    int pipeline = 1;  // DRR_TUNE_PIPELINE: host-bound batches are projected in two pieces, the copy of the first under the march of the
+                       // second; the value is the number of views in the second piece (0 = one piece)
     std::string err;
     // spectrum
     int n_bins = 0, M = 0;
@@ -531,7 +532,7 @@ int drr_set_tuning(drr_ctx* c, int key, int value) {  // tuning knobs (results d
     if (!c) return DRR_E_INVALID;
     if (key == DRR_TUNE_TEX_EIGHTHS && value >= 0 && value <= 8) { c->tex_eighths = value; return DRR_OK; }
     if (key == DRR_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) { c->variant = value; return DRR_OK; }
-    if (key == DRR_TUNE_PIPELINE && (value == 0 || value == 1)) { c->pipeline = value; return DRR_OK; }
+    if (key == DRR_TUNE_PIPELINE && value >= 0 && value <= 64) { c->pipeline = value; return DRR_OK; }
     return fail(c, DRR_E_INVALID, "drr_set_tuning: bad key/value %d/%d", key, value);
 }
 
@@ -1007,7 +1008,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
             c->minmax_cap = n_views;
         }
         CU(c, cudaMemsetAsync(c->d_const_flag, 0, sizeof(int), s));
-        const int first = n_views / 2;
+        const int first = n_views - (c->pipeline < n_views / 2 ? c->pipeline : n_views / 2);  // the last piece's copy is the exposed one
         for (int k = 0; k < 2; k++) {
             const int v0 = k ? first : 0, nv = k ? n_views - first : first;
             MarchParams Pk = P;

@@ -626,9 +626,10 @@ class Projector(object):
     def set_kernel_variant(self, variant: int):
         _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_KERNEL_VARIANT, int(variant)), self._h)
 
-    def set_pipeline(self, on: bool):
-        """Copy / compute pipeline of host-bound batches (on by default); results do not depend on it."""
-        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_PIPELINE, 1 if on else 0), self._h)
+    def set_pipeline(self, last_piece_views):
+        """Copy / compute pipeline of host-bound batches: views in the second piece (True = 1, the default; False / 0 = one piece).
+        Results do not depend on it."""
+        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_PIPELINE, int(last_piece_views)), self._h)
 
     def project_over_carm_range(self, *a, **k):
         raise DeprecationError("project_over_carm_range is deprecated. See README for alternatives.")

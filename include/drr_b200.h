@@ -97,8 +97,9 @@ int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int ai
  *                           5 or 8 (1..2 run as 3, 6..7 as 5).
  *   DRR_TUNE_KERNEL_VARIANT single-volume march: 0 = warp-cooperative shared-memory staging (default),
  *                           1 = per-ray register cell cache.
- *   DRR_TUNE_PIPELINE       1 (default): a batch of >= 4 views bound for host memory is projected in two halves, the
- *                           device-to-host copy of the first under the march of the second; 0: one piece. */
+ *   DRR_TUNE_PIPELINE       k > 0 (default 1): a batch of >= 4 views bound for host memory is projected in two pieces, the
+ *                           last k views (at most half) apart, so that the device-to-host copy of the first piece runs
+ *                           under the march of the second; 0: one piece. */
 #define DRR_TUNE_TEX_EIGHTHS 0
 #define DRR_TUNE_KERNEL_VARIANT 1
 #define DRR_TUNE_PIPELINE 2
