@@ -60,8 +60,8 @@ def test_single_volume_vs_reference_kernel_goldens(name):
 
 @pytest.mark.parametrize("name", ["multivol3", "multivol2_sameprio"])
 def test_multi_volume_vs_reference_kernel_goldens(name):
-    # priorities, same-priority averaging and the shared label cache quirk
-    _compare_with_golden(name, ("alu",))
+    # priorities, same-priority averaging and the shared label cache quirk, every sampler
+    _compare_with_golden(name, ("alu", "tex", "hybrid"))
 
 
 def test_full_size_c2_vs_reference_kernel_golden():
