@@ -1023,8 +1023,14 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
             if (post_flags & DRR_POST_CLIP) { CU(c, drr_launch_clip(img, npix * nv, intensity_upper_bound, s)); c->launches += 1; }
             if (post_flags & DRR_POST_NEGLOG) { CU(c, drr_launch_neglog(img, npix, nv, c->d_minmax + 2 * v0, 0.01f, s, c->d_const_flag)); c->launches += 2; }
             CU(c, cudaEventRecord(c->evp[3 * k + 2], s));
+        }
+        // the copies are queued after ALL the compute work: a pageable destination makes cudaMemcpyAsync block the host until its
+        // copy is done, and the second piece must already be on the GPU's queue by then
+        for (int k = 0; k < 2; k++) {
+            const int v0 = k ? first : 0, nv = k ? n_views - first : first;
             CU(c, cudaStreamWaitEvent(c->copy_stream, c->evp[3 * k + 2], 0));
-            CU(c, cudaMemcpyAsync(out_intensity + (size_t)v0 * npix, img, sizeof(float) * npix * nv, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(c, cudaMemcpyAsync(out_intensity + (size_t)v0 * npix, c->d_intensity + (size_t)v0 * npix, sizeof(float) * npix * nv,
+                                  cudaMemcpyDeviceToHost, c->copy_stream));
         }
         CU(c, cudaEventRecord(c->evp[6], c->copy_stream));
         CU(c, cudaMemcpyAsync(c->last_samples, c->d_samples, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
