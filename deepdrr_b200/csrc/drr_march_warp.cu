@@ -596,12 +596,14 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                                     if (USE_TEX) {
                                         c = __fadd_rn(c, rj[j]);
                                     } else if (STAGE_COEF) {
-                                        // cell-local coordinates: l = p - box_lo; exact for x >= 1
-                                        const float lx = __fsub_rn(x, b1x), ly = __fsub_rn(y, b1y), lz = __fsub_rn(z, b1z);
-                                        const float fbx = floorf(lx), fby = floorf(ly), fbz = floorf(lz);
+                                        // fraction inside the sample's own cell: p - floor(p) with p = x - 1 is x - floor(x), exact; the cell's
+                                        // place in the box from integers.  (x - b1 is NOT exact when the box starts in the clamped layers,
+                                        // b1 <= 0: it once moved a fraction of 191.49994 / 256 to 191.5000013 / 256, one fixed-point step.)
+                                        const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+                                        const float fbx = __fsub_rn(fx0, b1x), fby = __fsub_rn(fy0, b1y), fbz = __fsub_rn(fz0, b1z);
                                         const int idx = min((int)__fmaf_rn(__fmaf_rn(fbz, (float)ny, fby), (float)nx, fbx), MAXC - 1);
                                         const float4 cA = s_coef[idx], cB = s_coef[MAXC + idx];
-                                        c = __fadd_rn(c, hw_trilinear_cell2(__fsub_rn(lx, fbx), __fsub_rn(ly, fby), __fsub_rn(lz, fbz), cA, cB));
+                                        c = __fadd_rn(c, hw_trilinear_cell2(__fsub_rn(x, fx0), __fsub_rn(y, fy0), __fsub_rn(z, fz0), cA, cB));
                                     }
                                 } else {
                                     w_slow_sample<NM, USE_TEX>(vol, x, y, z, (tt == 0 || tt == last) ? 0.5f : 1.0f, acc[0], rj[j], USE_TEX);  // K.cu:537

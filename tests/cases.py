@@ -63,3 +63,49 @@ class MatrixProjection:
             fx = fy = 1.0
 
         self.intrinsic = _K()
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    a, b, c, d = q
+    return np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                     [2 * (b * c + a * d), a * a - b * b + c * c - d * d, 2 * (c * d - a * b)],
+                     [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
+
+
+def random_single_volume_scene(rng, it, build=True):
+    """Scene number ``it`` of the randomised parity runs (tools/fuzz_single.py): a thorax phantom of random shape, spacing and pose
+    seen by a random camera -- source inside the volume (it % 4 == 0), grazing along a face (1) or anywhere around it (2, 3), coarse
+    to fine detectors, short or unbounded ``max_ray_length``.  Consumes the same random numbers whether or not the volume is built,
+    so that one iteration of a long run can be replayed."""
+    from deepdrr_b200 import geo
+
+    shape = tuple(int(x) for x in rng.integers(24, 72, size=3))
+    spacing = tuple(rng.uniform(0.6, 8.0, size=3))
+    vseed = int(rng.integers(1 << 30))
+    vrot, vtr = _random_rotation(rng), rng.uniform(-40, 40, size=3)
+    v = st = None
+    if build:
+        v = phantoms.thorax_volume(shape, spacing, seed=vseed)
+        v.rotate(vrot)
+        v.translate(vtr)
+        st = SceneTables([v], "90KV_AL40")
+    W, H = int(rng.integers(17, 120)), int(rng.integers(9, 100))
+    pixel = float(rng.choice([0.2, 0.8, 2.0, 6.0]))
+    sdd = float(rng.uniform(300, 1500))
+    k = geo.CameraIntrinsicTransform.from_sizes((W, H), pixel, sdd)
+    extent = np.array(shape) * np.array(spacing)
+    mode = it % 4
+    if mode == 0:    # source inside the volume
+        source = rng.uniform(-0.3, 0.3, size=3) * extent
+    elif mode == 1:  # grazing: looking along a face
+        source = np.array([0.0, -extent[1], 0.5 * extent[2]]) + rng.normal(size=3)
+    else:
+        source = rng.normal(size=3)
+        source = source / np.linalg.norm(source) * float(rng.uniform(0.6, 3.0)) * extent.max()
+    direction = -source + rng.normal(size=3) * 0.2 * extent.max() if mode != 0 else rng.normal(size=3)
+    up = rng.normal(size=3)
+    pose = phantoms.look_at_projection(source, direction, up, k)
+    mrl = float(rng.choice([4 * sdd, 0.7 * np.linalg.norm(source) + 10.0, 1e5]))
+    return {"volume": v, "tables": st, "W": W, "H": H, "pixel": pixel, "sdd": sdd, "k": k, "pose": pose, "mrl": mrl, "mode": mode, "shape": shape}

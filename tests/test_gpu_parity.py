@@ -489,3 +489,34 @@ def test_pipelined_host_batches_equal_single_piece_batches():
         raw = p.project(*poses, max_ray_length=carm.max_ray_length).copy()
         p.set_pipeline(False)
         assert np.array_equal(raw, p.project(*poses, max_ray_length=carm.max_ray_length))
+
+
+def test_fma_pipe_sampler_on_boxes_that_start_in_the_clamped_layers():
+    """Regression: scenes 110, 170, 815 and 1115 of `tools/fuzz_single.py 1500 11`.  The general-segment path of the FMA-pipe sampler
+    took a sample's fraction as (x - box origin) - floor(...), which is not exact when the staged box starts in the clamped cell
+    layers (origin <= 0): a fraction of 191.49994 / 256 became 191.5000013 / 256, one fixed-point step of the texture unit's
+    coordinate, 0.9 % of that sample -- 3.5e-5 of a pure-air pixel's line integral.  Now x - floor(x), exact."""
+    from oracle import ref_gpu
+
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not shipped")
+    rng = np.random.default_rng(11)
+    wanted = {110, 170, 815, 1115}
+    for it in range(1116):
+        sc = cases.random_single_volume_scene(rng, it, build=it in wanted)
+        if it not in wanted:
+            continue
+        v, st, W, H = sc["volume"], sc["tables"], sc["W"], sc["H"]
+        w2i, src, ijk = geo.pose_arrays(sc["pose"], [v])
+        ref = ref_gpu.RefProjector([v.data], st.labels, st.M, lineint=True)
+        li = ref.line_integrals(W, H, 0.1, w2i, src, ijk, sc["mrl"])
+        ref.close()
+        for sampler in ("alu", "hybrid"):
+            with Projector(v, spectrum="90KV_AL40", neglog=False, camera_intrinsics=sc["k"], source_to_detector_distance=sc["sdd"], sampler=sampler) as p:
+                area = p.project_line_integrals(sc["pose"], max_ray_length=sc["mrl"])[0]
+            for m in range(st.M):
+                mask = li[m] > 0
+                assert np.all(area[m][~mask] == 0)
+                if mask.any():
+                    err = cases.rel_err(area[m], li[m])[mask].max()
+                    assert err <= 2e-6, f"scene {it} [{sampler}] material {m}: {err:.2e}"
