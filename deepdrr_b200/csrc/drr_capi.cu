@@ -64,6 +64,7 @@ struct ScatterTables {
     const float* inv_rho_nom;
     const float* majorant;
     const int* mat_of_label;
+    const float* s0;
 };
 struct ScatterParams {
     ScatterTables T;
@@ -660,6 +661,26 @@ int drr_set_scatter_tables(drr_ctx* c, int n_mat, int n_e, float e0, float de, c
     if ((rc = up(inv_rho.data(), sizeof(float) * n_mat, &p))) return rc; c->sc.inv_rho_nom = (const float*)p;
     if ((rc = up(maj.data(), sizeof(float) * n_e, &p))) return rc; c->sc.majorant = (const float*)p;
     if ((rc = up(mat_of_label, sizeof(int) * c->M, &p))) return rc; c->sc.mat_of_label = (const int*)p;
+    {   // S(E, theta = pi) of the impulse-approximation Compton model per table material on the energy grid (see sample_compton)
+        std::vector<float> s0((size_t)n_mat * n_e);
+        const double REV = 510998.918, D2 = 1.4142135623731, D1 = 0.70710678118655;
+        for (int m = 0; m < n_mat; m++)
+            for (int e = 0; e < n_e; e++) {
+                const double E = (double)e0 + (double)de * e;
+                double sum = 0.0;
+                for (int i = 0; i < nshell[m]; i++) {
+                    const double f = compton[((size_t)m * 30 + i) * 3], U = compton[((size_t)m * 30 + i) * 3 + 1], J = compton[((size_t)m * 30 + i) * 3 + 2];
+                    if (!(U < E)) continue;
+                    const double aux = E * (E - U) * 2.0;
+                    const double pz = J * (aux - REV * U) / (REV * sqrt(aux + aux + U * U));
+                    const double q = pz > 0.0 ? D1 + D2 * pz : D1 - D2 * pz;
+                    const double h = 0.5 * exp(0.5 - q * q);
+                    sum += f * (pz > 0.0 ? 1.0 - h : h);
+                }
+                s0[(size_t)m * n_e + e] = (float)(sum * 1.001);
+            }
+        if ((rc = up(s0.data(), sizeof(float) * s0.size(), &p))) return rc; c->sc.s0 = (const float*)p;
+    }
     c->sc.n_mat = n_mat; c->sc.n_e = n_e; c->sc.e0 = e0; c->sc.de = de;
     // spectrum CDF of max(pdf, 0) (the last bin of the reference's spectra is negative)
     std::vector<float> cdf(c->n_bins);

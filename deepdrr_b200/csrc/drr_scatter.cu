@@ -32,6 +32,7 @@ struct ScatterTables {
     const float* inv_rho_nom;    // [n_mat]
     const float* majorant;       // [n_e]: max over materials of rho_max / rho_nom / mfp_total  (1/mm)
     const int* mat_of_label;     // [M] global material index -> table material
+    const float* s0;             // [n_mat][n_e]: incoherent scattering function at theta = pi (its maximum), x 1.001
 };
 
 struct ScatterParams {
@@ -133,9 +134,16 @@ __device__ float sample_compton(const ScatterTables& T, int mat, float& E, curan
         const float h = 0.5f * expf(D12 - q * q);
         return pz > 0.0f ? 1.0f - h : h;
     };
-    float s0 = 0.0f;  // S(E, theta = pi)
-    for (int i = 0; i < ns; i++)
-        if (C[3 * i + 1] < E) s0 += C[3 * i] * profile_cdf(i, 2.0f);
+    // S(E, theta = pi), the maximum of the incoherent scattering function over the angle: tabulated on the energy grid by the host
+    // (it only normalises the rejection; a third of the sampler's shell-profile evaluations otherwise)
+    float s0;
+    {
+        const float f = (E - T.e0) / T.de;
+        const int i = max(0, min((int)f, T.n_e - 2));
+        const float w = fminf(fmaxf(f - (float)i, 0.0f), 1.0f);
+        const float* a = T.s0 + (size_t)mat * T.n_e + i;
+        s0 = a[0] + w * (a[1] - a[0]);
+    }
     float rn[30], pac[30];
     float tau = 1.0f, cdt1 = 0.0f, sfun = 0.0f;
     for (int tries = 0; tries < 200; tries++) {
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(128) scatter_kernel(const __grid_constant__ Sc
             // the volume this point belongs to: smallest priority value among the volumes that contain it
             int best = -1, best_pr = 0x7fffffff;
             size_t o = 0;
-            for (int vv = 0; vv < P.V; vv++) {
+            for (int vv = 0; vv < P.V; vv++) {  // (V == 1: the loop runs once; t <= t1 already says "inside" up to rounding)
                 if (!P.enabled[vv] || P.priority[vv] >= best_pr) continue;
                 const float* A = P.ijk[vv];
                 const float qi = A[0] * X + A[1] * Y + A[2] * Z + A[3], qj = A[4] * X + A[5] * Y + A[6] * Z + A[7],

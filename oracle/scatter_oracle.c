@@ -29,6 +29,7 @@ typedef struct {
     const float* inv_rho_nom;  /* [n_mat] */
     const float* majorant;     /* [n_e] */
     const int* mat_of_label;   /* [M] */
+    const float* s0;           /* [n_mat][n_e]: S(E, theta = pi) x 1.001, the normalisation of the Compton rejection */
     int V;                     /* volumes; a point inside several belongs to the one with the smallest priority value */
     int priority[8], enabled[8];
     const float* dens[8];      /* [ni][nj][nk] g/cm^3 (NumPy order of Volume.data) */
@@ -150,9 +151,20 @@ static float sample_compton(const sc_scene* S, int mat, float* Eio, philox* st) 
     float a1 = logf(ek2), a2 = a1 + 2.0f * ek * (1.0f + ek) * taum2;
     const float* C = S->compton + (size_t)mat * 30 * 3;
     int ns = S->nshell[mat];
-    float s0 = 0.0f;
-    for (int i = 0; i < ns; i++)
-        if (C[3 * i + 1] < E) s0 += C[3 * i] * profile_cdf(C, i, E, 2.0f);
+    float s0;  /* S(E, pi) from the table (compton_samples: computed here) */
+    if (S->s0) {
+        float f = (E - S->e0) / S->de;
+        int i = (int)f;
+        if (i < 0) i = 0;
+        if (i > S->n_e - 2) i = S->n_e - 2;
+        float w = fminf(fmaxf(f - (float)i, 0.0f), 1.0f);
+        const float* a = S->s0 + (size_t)mat * S->n_e + i;
+        s0 = a[0] + w * (a[1] - a[0]);
+    } else {
+        s0 = 0.0f;
+        for (int i = 0; i < ns; i++)
+            if (C[3 * i + 1] < E) s0 += C[3 * i] * profile_cdf(C, i, E, 2.0f);
+    }
     float rn[30], pac[30], tau = 1.0f, cdt1 = 0.0f, sfun = 0.0f;
     for (int tries = 0; tries < 200; tries++) {
         if (philox_uniform(st) * a2 < a1) tau = powf(taumin, philox_uniform(st));

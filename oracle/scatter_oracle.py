@@ -20,7 +20,7 @@ _lib = None
 class _Scene(ctypes.Structure):
     _fields_ = [("n_mat", ctypes.c_int), ("n_e", ctypes.c_int), ("e0", ctypes.c_float), ("de", ctypes.c_float),
                 ("mfp", ctypes.c_void_p), ("rita", ctypes.c_void_p), ("compton", ctypes.c_void_p), ("nshell", ctypes.c_void_p),
-                ("inv_rho_nom", ctypes.c_void_p), ("majorant", ctypes.c_void_p), ("mat_of_label", ctypes.c_void_p),
+                ("inv_rho_nom", ctypes.c_void_p), ("majorant", ctypes.c_void_p), ("mat_of_label", ctypes.c_void_p), ("s0", ctypes.c_void_p),
                 ("V", ctypes.c_int), ("priority", ctypes.c_int * 8), ("enabled", ctypes.c_int * 8),
                 ("dens", ctypes.c_void_p * 8), ("lab", ctypes.c_void_p * 8), ("shape", (ctypes.c_int * 3) * 8),
                 ("ijk", (ctypes.c_float * 12) * 8), ("p_idx", ctypes.c_float * 12), ("w2i", ctypes.c_float * 9), ("src", ctypes.c_float * 3),
@@ -96,6 +96,20 @@ def simulate(volumes, all_materials, spectrum_energies_keV, spectrum_pdf, proj, 
         mu = (rho_max[l] * inv_rho[m]).astype(np.float32) / mfp[m, :, 3]
         maj = np.maximum(maj, mu.astype(np.float32))
     maj[~(maj > 0)] = np.float32(1e-6)
+    # S(E, theta = pi) of every table material on the energy grid, x 1.001 (float64, then float32): the rejection's normalisation
+    s0 = np.zeros((len(names), len(e)), dtype=np.float64)
+    REV, D2, D1 = 510998.918, 1.4142135623731, 0.70710678118655
+    for m in range(len(names)):
+        for i in range(int(nshell[m])):
+            f, U, J = (float(x) for x in comp[m, i])
+            on = U < e
+            aux = e * (e - U) * 2.0
+            with np.errstate(invalid="ignore"):
+                pz = J * (aux - REV * U) / (REV * np.sqrt(aux + aux + U * U))
+            q = np.where(pz > 0, D1 + D2 * pz, D1 - D2 * pz)
+            h = 0.5 * np.exp(0.5 - q * q)
+            s0[m] += np.where(on, f * np.where(pz > 0, 1.0 - h, h), 0.0)
+    s0 = np.ascontiguousarray((s0 * 1.001).astype(np.float32))
     pdf = np.asarray(spectrum_pdf, dtype=np.float32)
     pos = np.where(pdf > 0, pdf.astype(np.float64), 0.0)
     cdf = (np.cumsum(pos) / pos.sum()).astype(np.float32)
@@ -107,9 +121,10 @@ def simulate(volumes, all_materials, spectrum_energies_keV, spectrum_pdf, proj, 
     src = np.ascontiguousarray(np.asarray(proj.center_in_world, dtype=np.float64).reshape(-1)[:3], dtype=np.float32)
     S = _Scene()
     S.n_mat, S.n_e, S.e0, S.de = len(names), len(e), float(e[0]), float(e[1] - e[0])
-    keep = [mfp, rita, comp, nshell, inv_rho, maj, mol, dens, labels, ekev, cdf]
+    keep = [mfp, rita, comp, nshell, inv_rho, maj, mol, dens, labels, ekev, cdf, s0]
     S.mfp, S.rita, S.compton, S.nshell = mfp.ctypes.data, rita.ctypes.data, comp.ctypes.data, nshell.ctypes.data
     S.inv_rho_nom, S.majorant, S.mat_of_label = inv_rho.ctypes.data, maj.ctypes.data, mol.ctypes.data
+    S.s0 = s0.ctypes.data
     S.V = V
     for v in range(V):
         S.priority[v], S.enabled[v] = int(priorities[v]), int(bool(getattr(volumes[v], "enabled", True)))
