@@ -588,7 +588,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", action="store_true", help="append C3 / C4 timings under 'secondary' (extra projectors after the headline run)")
     ap.add_argument("--no-secondary", action="store_true", help="accepted for compatibility (the default now)")
-    ap.add_argument("--cpu-crop", type=int, default=512, help="side of the centred pixel crop the CPU oracle marches for cpu_baseline")
+    ap.add_argument("--cpu-crop", type=int, default=768, help="side of the centred pixel crop the CPU oracle marches for cpu_baseline")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2: the headline projection metric; c3: CT + two K-wire volumes, 384x384; c5: Monte Carlo scatter photons/s")
     ap.add_argument("--photons", type=float, default=1e8, help="--config c5: photons per view")
