@@ -320,7 +320,9 @@ def run_ours(args):
     if cap:  # what binds, from the committed ncu capture of this command (stale if the kernel changed since: see its "head")
         binding["from_committed_capture"] = {k: cap.get(k) for k in ("_file", "head", "kernel", "issue_slot_utilisation", "tex_request_cycles_pct", "pipe_fma_pct",
                                                                      "pipe_alu_pct", "shared_pipe_wavefronts_pct", "avg_active_lanes", "l1tex_hit_pct",
-                                                                     "l2_hit_pct", "warps_active_pct", "registers_per_thread")}
+                                                                     "l2_hit_pct", "warps_active_pct", "registers_per_thread", "l1tex_throughput_pct",
+                                                                     "l1tex_tex_data_pipe_wavefronts_pct", "l1tex_filter_wavefronts_pct",
+                                                                     "l1tex_lsu_data_pipe_wavefronts_pct", "l2_GBps", "dram_GBps")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is reported at N = 1 only

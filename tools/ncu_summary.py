@@ -101,6 +101,18 @@ if a.json:
           "pipe_xu_pct": f("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
           "registers_per_thread": f("launch__registers_per_thread"), "grid": f("launch__grid_size"), "block": f("launch__block_size"),
           "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
-          "dram_throughput_pct": f("FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed") or f("dram__throughput.avg.pct_of_peak_sustained_elapsed")}
+          "dram_throughput_pct": f("FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed") or f("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+          # what binds: the texture data pipe of the L1TEX unit (wavefronts per cycle), its filter stage, the LSU data pipe (shared memory)
+          "l1tex_throughput_pct": f("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+          "l1tex_tex_data_pipe_wavefronts_pct": f("l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+          "l1tex_filter_wavefronts_pct": f("l1tex__f_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+          "l1tex_lsu_data_pipe_wavefronts_pct": f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+          "tex_output_wavefronts": f("l1tex__t_output_wavefronts_pipe_tex_mem_texture.sum"),
+          "tex_requests": f("l1tex__t_requests_pipe_tex_mem_texture.sum"),
+          "l2_bytes_per_launch": (f("lts__t_sectors.sum") or 0) * 32.0,
+          "l2_throughput_pct": f("lts__throughput.avg.pct_of_peak_sustained_elapsed")}
+    if js["duration_ms_under_ncu"]:
+        js["l2_GBps"] = js["l2_bytes_per_launch"] / js["duration_ms_under_ncu"] / 1e6
+        js["dram_GBps"] = js["march_dram_bytes_per_launch"] / js["duration_ms_under_ncu"] / 1e6
     json.dump(js, open(a.json, "w"), indent=1)
     print("wrote", a.json)
