@@ -204,6 +204,7 @@ struct drr_ctx {
     int attenuate_outside = 0, air_index = 0, sampler = DRR_SAMPLER_HYBRID;
     int tex_eighths = 4;
     int variant = 0;  // 0: warp-cooperative march (default), 1: per-ray register-cell march
+    int lane_quads = 2;  // DRR_TUNE_LANE_QUADS: 0 / 1, 2 = the library's choice (1)
     // mesh buffers (device pointers, possibly owned)
     int mesh_layers = 0, max_hits = 0, n_mesh_mats = 0;
     const float* hit_alphas = nullptr;
@@ -534,6 +535,7 @@ int drr_set_tuning(drr_ctx* c, int key, int value) {  // tuning knobs (results d
     if (key == DRR_TUNE_TEX_EIGHTHS && value >= 0 && value <= 8) { c->tex_eighths = value; return DRR_OK; }
     if (key == DRR_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) { c->variant = value; return DRR_OK; }
     if (key == DRR_TUNE_PIPELINE && value >= 0 && value <= 64) { c->pipeline = value; return DRR_OK; }
+    if (key == DRR_TUNE_LANE_QUADS && value >= 0 && value <= 2) { c->lane_quads = value; return DRR_OK; }
     return fail(c, DRR_E_INVALID, "drr_set_tuning: bad key/value %d/%d", key, value);
 }
 
@@ -836,8 +838,7 @@ int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n
 // The warp-cooperative kernel stages the voxel cells an 8x4-pixel tile touches; it pays when neighbouring
 // rays are closer than a few voxels.  Estimate the tile's footprint at the volume centre for view 0 and
 // fall back to the per-ray kernel for coarse detectors / strongly magnified set-ups.
-static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
-    if (c->variant != 0) return c->variant;
+static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
     const VolHost& v = c->vols[0];
     auto dir = [&](float u, float vv, float* d) {
         float r[3];
@@ -853,7 +854,12 @@ static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, co
     float alpha_c = dd > 0 ? (ctr[0] * d0[0] + ctr[1] * d0[1] + ctr[2] * d0[2]) / dd : 0.0f;
     float spread = 0.0f;
     for (int a = 0; a < 3; a++) spread = fmaxf(spread, fabsf(alpha_c * (d1[a] - d0[a])));
-    return spread > 4.0f ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
+    return spread;
+}
+
+static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
+    if (c->variant != 0) return c->variant;
+    return tile_spread(c, w2i, src, ijk, W, H) > 4.0f ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
 }
 
 // Slack of the lock-step kernels' staged boxes and window tests for this batch (see drr_march_warp.cu).  A segment of S steps is
@@ -1016,6 +1022,7 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
         P.tex_eighths = sampler == DRR_SAMPLER_ALU ? 0 : (sampler == DRR_SAMPLER_TEX ? 8 : c->tex_eighths);
     }
     const bool lockstep_ok = V > 0 && march_slack(c, n_views, src_ijk, ijk_from_world, max_ray_length, P);
+    P.lane_quads = c->lane_quads == 2 ? 1 : c->lane_quads;  // 2 x 2 lane groups (see drr_march_warp.cu: lane_u); single-volume kernel only
     // ---- host-bound single-volume batches: two halves, the device-to-host copy of the first under the march of the second -----
     // (projector.py:786-792 copies every view back before the next one starts; here only the second half's copy is exposed)
     const bool lockstep_single = single && h_has_cells(c) && (c->variant == 0 ? lockstep_ok : true) &&

@@ -52,6 +52,9 @@
 #define SMB 4                          // ... and resident blocks per SM it is compiled for (register budget 65536 / (32 SWB SMB))
 #endif
 #define MULTI_MAXV 4                   // volumes the multi-volume variant handles
+#ifndef FAST_ROTATE
+#define FAST_ROTATE 1                  // fast segments rotate only the ray state they use
+#endif
 #ifndef RAYS_PER_LANE
 #define RAYS_PER_LANE 2                // single-volume kernel: a warp walks an 8 x (4 * RAYS_PER_LANE) pixel tile
 #endif
@@ -61,6 +64,18 @@
 // alpha and finest voxel pitch (drr_capi.cu: march_slack) -- 0.01 / 0.0125 voxel and 0.01 mm for C2 -- and routes scenes that
 // would need more than a quarter voxel to the per-ray kernels.
 
+// lane -> pixel inside an 8 x 4 block.  The texture unit filters the lanes of a fetch in groups of four (lanes 4i .. 4i+3, two
+// data-pipe wavefronts per group and fetch at best).  With `quads` such a group is a 2 x 2 block of pixels instead of a 4 x 1 run:
+// its rays share a cell more often and the fetches cost fewer wavefronts -- 1 to 2 % of the single-volume march at every ray
+// spacing from 0.12 (C2, 14.15 -> 14.02 ms per view) to 0.3 voxel (tools/quads_sweep.py).  The multi-volume kernel loses 3 % with
+// it on C3 (1.01 -> 1.05 ms) and keeps the row-major layout.
+__device__ __forceinline__ int lane_u(int lane, bool quads) {
+    return quads ? ((lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4)) : (lane & (TILE_W - 1));  // quads: lane bits 0, 2, 4
+}
+__device__ __forceinline__ int lane_v(int lane, bool quads) {
+    return quads ? (((lane >> 1) & 1) | ((lane >> 2) & 2)) : (lane >> 3);                         // quads: lane bits 1, 3
+}
+
 // tile id -> view and this lane's pixel (8x4 tiles, row-major per view)
 __device__ __forceinline__ void tile_pixel(const MarchParams& P, unsigned tile, int lane, int& view, int& udx, int& vdx) {
     const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
@@ -68,8 +83,8 @@ __device__ __forceinline__ void tile_pixel(const MarchParams& P, unsigned tile, 
     view = (int)(tile / tiles_per_view);
     const unsigned tv = tile - (unsigned)view * tiles_per_view;
     const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
-    udx = tx * TILE_W + (lane & (TILE_W - 1));
-    vdx = ty * TILE_H + (lane >> 3);
+    udx = tx * TILE_W + lane_u(lane, false);
+    vdx = ty * TILE_H + lane_v(lane, false);
 }
 
 // ---- running-total bookkeeping (same order of fp32 adds as K.cu:544-546) ------------------------
@@ -237,6 +252,20 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                 for (int r = 0; r + 1 < R; r++) acc[r][m] = acc[r + 1][m];
                 acc[R - 1][m] = a0;
             }
+        }
+    };
+    // fast segments touch only the direction, alpha and the checked-out total of a ray (the per-material totals only when a lane
+    // changes material: then through the pass index)
+    auto rotate_fast = [&]() {
+        static_assert(!FAST_ROTATE || R <= 2, "the pass index picks the totals of ray R - 1");
+        if (R > 1) {
+            auto rot = [&](auto& x) {
+                auto x0 = x[0];
+#pragma unroll
+                for (int r = 0; r + 1 < R; r++) x[r] = x[r + 1];
+                x[R - 1] = x0;
+            };
+            rot(rdx); rot(rdy); rot(rdz); rot(alpha); rot(cur); rot(live);
         }
     };
 
@@ -464,10 +493,22 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
             const int t_stop = t + S;
 #pragma unroll 1
             for (int pass = 0; pass < R; pass++) {
+#if FAST_ROTATE
+                if (live[0] != code0) {
+                    if (R == 1 || pass == 0) {
+                        w_checkin<NM>(cur[0], live[0], acc[0]);
+                        cur[0] = w_checkout<NM>(code0, live[0], acc[0]);
+                    } else {
+                        w_checkin<NM>(cur[0], live[0], acc[R - 1]);
+                        cur[0] = w_checkout<NM>(code0, live[0], acc[R - 1]);
+                    }
+                }
+#else
                 if (live[0] != code0) {
                     w_checkin<NM>(cur[0], live[0], acc[0]);
                     cur[0] = w_checkout<NM>(code0, live[0], acc[0]);
                 }
+#endif
                 const float dxr = rdx[0], dyr = rdy[0], dzr = rdz[0];
                 float al = alpha[0], c = cur[0];
                 int tt = t;
@@ -522,7 +563,11 @@ __device__ __forceinline__ void march_core(const VolDev& vol, const float step, 
                     }
                 }
                 alpha[0] = al; cur[0] = c;
+#if FAST_ROTATE
+                rotate_fast();
+#else
                 rotate();
+#endif
             }
             t = t_stop;
             continue;
@@ -677,7 +722,7 @@ __global__ void __launch_bounds__(32 * SWB, SMB) march_warp_kernel(const __grid_
         const unsigned view = tile / tiles_per_view;
         const unsigned tv = tile - view * tiles_per_view;
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
-        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * (TILE_H * R) + (lane >> 3);
+        const int udx = tx * TILE_W + lane_u(lane, P.lane_quads != 0), vdx = ty * (TILE_H * R) + lane_v(lane, P.lane_quads != 0);
         // every tile uses the same sampler mix, and the mix is a function of the step index only, so results do not
         // depend on scheduling
         float acc[R][NM];
@@ -739,7 +784,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MIN_BLOCKS) march_multi_
         const unsigned view = tile / tiles_per_view;
         const unsigned tv = tile - view * tiles_per_view;
         const int ty = tv / tiles_x, tx = tv - ty * tiles_x;
-        const int udx = tx * TILE_W + (lane & (TILE_W - 1)), vdx = ty * TILE_H + (lane >> 3);
+        const int udx = tx * TILE_W + lane_u(lane, false), vdx = ty * TILE_H + lane_v(lane, false);
         const bool ok = udx < P.W && vdx < P.H;
         const ViewDev& vw = P.views[view];
 

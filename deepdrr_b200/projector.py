@@ -631,5 +631,10 @@ class Projector(object):
         Results do not depend on it."""
         _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_PIPELINE, int(last_piece_views)), self._h)
 
+    def set_lane_quads(self, mode: int):
+        """Lane-to-pixel layout of the single-volume lock-step march: 1 = 2 x 2 groups, 0 = 4 x 1 runs, 2 = the library's choice (default).
+        Results do not depend on it."""
+        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_LANE_QUADS, int(mode)), self._h)
+
     def project_over_carm_range(self, *a, **k):
         raise DeprecationError("project_over_carm_range is deprecated. See README for alternatives.")
