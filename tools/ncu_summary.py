@@ -14,6 +14,7 @@ ap.add_argument("rep")
 ap.add_argument("--json")
 ap.add_argument("--views", type=int, default=8)
 ap.add_argument("--command", default="")
+ap.add_argument("--head", default="", help="commit (and a word on the kernel) the capture was taken at; bench.py quotes it")
 ap.add_argument("--algorithmic-bytes-per-view", type=int, default=543162368)
 a = ap.parse_args()
 
@@ -87,7 +88,7 @@ if a.json:
         return None if v is None else v * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3, "nsecond": 1e-6}.get(u, 1e-6)
     rd, wr = in_bytes("dram__bytes_read.sum"), in_bytes("dram__bytes_write.sum")
     inst, cyc = f("smsp__inst_executed.sum"), f("sm__cycles_elapsed.avg")
-    js = {"command": a.command, "kernel": m.get("Kernel Name", ""), "views_per_launch": a.views,
+    js = {"command": a.command, "head": a.head, "kernel": m.get("Kernel Name", ""), "views_per_launch": a.views,
           "march_dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_bytes_read": rd, "dram_bytes_write": wr,
           "algorithmic_bytes_per_launch": a.algorithmic_bytes_per_view * a.views, "duration_ms_under_ncu": in_ms("gpu__time_duration.sum"),
           "warp_instructions": inst, "sm_cycles": cyc, "tex_lane_fetches_per_launch": tex_lane_fetches,
