@@ -56,8 +56,7 @@ struct ScatterParams {
 };
 
 // Philox4x32-10 exactly as cuRAND drives it for curand_init(seed, subsequence, 0) + curand_uniform: key = seed, counter =
-// (block, 0, subsequence lo, subsequence hi), four outputs per block handed out in order and the next block computed as soon as
-// the fourth is taken, uniform = x * 2^-32 + 2^-33 in (0, 1].  Restated here: 8 words of state per photon instead of cuRAND's
+// (block, 0, subsequence lo, subsequence hi), four outputs per block handed out in order, uniform = x * 2^-32 + 2^-33 in (0, 1].  Restated here: 8 words of state per photon instead of cuRAND's
 // struct, and the ten rounds out of line (they were inlined at a dozen call sites, 46 instructions each, in a kernel whose code did
 // not fit the instruction cache).  The block counter is 32 bits: a history would need 2^34 draws to wrap it.
 // (Tried: carrying the next block as well and computing it only where the warp is convergent, so that the rounds run with half
@@ -88,7 +87,7 @@ __device__ __forceinline__ void philox_start(Philox& s, unsigned long long seed,
 }
 __device__ __forceinline__ float philox_uniform(Philox& s) {
     const unsigned x = s.pos == 0 ? s.o0 : (s.pos == 1 ? s.o1 : (s.pos == 2 ? s.o2 : s.o3));
-    if (++s.pos == 4) {
+    if (++s.pos == 4) {  // as cuRAND: the next block is computed as soon as the fourth output is taken
         s.c0 += 1;
         const uint4 o = philox_block(s.c0, s.c2, s.c3, s.k0, s.k1);
         s.o0 = o.x; s.o1 = o.y; s.o2 = o.z; s.o3 = o.w;
@@ -96,18 +95,8 @@ __device__ __forceinline__ float philox_uniform(Philox& s) {
     }
     return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
-
-__device__ __forceinline__ void mfp_lookup(const ScatterTables& T, int mat, float E, float& iray, float& ico, float& itot, float& pmax) {
-    float f = (E - T.e0) / T.de;
-    int i = max(0, min((int)f, T.n_e - 2));
-    float w = fminf(fmaxf(f - (float)i, 0.0f), 1.0f);
-    const float* a = T.mfp + ((size_t)mat * T.n_e + i) * 5;
-    const float* b = a + 5;
-    iray = 1.0f / (a[0] + w * (b[0] - a[0]));
-    ico = 1.0f / (a[1] + w * (b[1] - a[1]));
-    itot = 1.0f / (a[3] + w * (b[3] - a[3]));
-    pmax = a[4] + w * (b[4] - a[4]);
-}
+// (Tried: computing the next block only when the fifth output is asked for, so that a draw never ends in a call while the voxel
+// reads of a tracking step are in flight -- the call waits for them.  5.55e8 -> 5.1e8 photons/s: slower.)
 
 __device__ __forceinline__ void rotate_dir(float& dx, float& dy, float& dz, float cost, float phi) {
     float sint = sqrtf(fmaxf(0.0f, 1.0f - cost * cost));
@@ -166,7 +155,7 @@ __device__ float sample_rayleigh(const ScatterTables& T, int mat, float E, float
 // them needs.  `compton_finish` is steps 2 and 3 for an accepted try: returns cos(theta) and replaces E.
 struct ComptonTry {
     float tau, cdt1, sfun;
-    float rn[30], pac[30];
+    float rn[32], pac[32];  // up to 30 shells; read four at a time
 };
 
 __device__ __forceinline__ bool compton_try(const ScatterTables& T, int mat, float E, Philox& st, ComptonTry& c) {
@@ -219,7 +208,12 @@ __device__ __forceinline__ float compton_finish(const ScatterTables& T, int mat,
     for (int tries = 0; tries < 200; tries++) {
         const float tst = sfun * philox_uniform(st);
         int ish = ns - 1;
-        for (int i = 0; i < ns; i++) if (c.pac[i] > tst) { ish = i; break; }
+        // first shell whose cumulative probability exceeds tst; four loads of the (local-memory) table in flight at a time
+        for (int i = 0; i < ns; i += 4) {
+            const float p0 = c.pac[i], p1 = c.pac[i + 1], p2 = c.pac[i + 2], p3 = c.pac[i + 3];
+            const int hit = p0 > tst ? 0 : ((i + 1 < ns && p1 > tst) ? 1 : ((i + 2 < ns && p2 > tst) ? 2 : ((i + 3 < ns && p3 > tst) ? 3 : 4)));
+            if (hit < 4) { ish = i + hit; break; }
+        }
         const float a = philox_uniform(st) * c.rn[ish];
         if (a < 0.5f) pzomc = (D1 - sqrtf(D12 - logf(a + a))) / (D2 * C[3 * ish + 2]);
         else pzomc = (sqrtf(D12 - logf(2.0f - a - a)) - D1) / (D2 * C[3 * ish + 2]);
@@ -448,12 +442,19 @@ __global__ void __launch_bounds__(32 * SC_WARPS, SC_MIN_BLOCKS) scatter_kernel(c
                             o = ((size_t)vk * vol.nj + vj) * vol.ni + vi;
                         }
                         if (best >= 0) {  // (between the volumes is vacuum: every interaction there is virtual)
-                            mat = T.mat_of_label[__ldg(P.vol[best].lab + o)];
-                            float rho = __ldg(P.vol[best].dens + o);
-                            float iray, ico, itot;
-                            mfp_lookup(T, mat, E, iray, ico, itot, pmax);
+                            // the two voxel reads (a random place in the volume: the long wait of a step) are issued first and
+                            // the draw that decides real / virtual is taken while they are in flight
+                            const unsigned lb = __ldg(P.vol[best].lab + o);
+                            const float rho = __ldg(P.vol[best].dens + o);
+                            const float u_virtual = philox_uniform(st);
+                            mat = T.mat_of_label[lb];
+                            // total inverse mean free path first (five out of six steps are virtual and need nothing else)
+                            const float* ma = T.mfp + ((size_t)mat * T.n_e + ie) * 5;
+                            const float itot = 1.0f / (ma[3] + wq * (ma[8] - ma[3]));
                             float scale = rho * T.inv_rho_nom[mat];
-                            if (!(philox_uniform(st) * smax >= itot * scale)) {  // a real interaction
+                            if (!(u_virtual * smax >= itot * scale)) {  // a real interaction
+                                const float iray = 1.0f / (ma[0] + wq * (ma[5] - ma[0])), ico = 1.0f / (ma[1] + wq * (ma[6] - ma[1]));
+                                pmax = ma[4] + wq * (ma[9] - ma[4]);
                                 float r = philox_uniform(st) * itot;
                                 x = X; y = Y; z = Z;  // move the photon to the interaction point
                                 if (r < iray) state = RAYLEIGH;
