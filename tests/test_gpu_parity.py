@@ -491,6 +491,24 @@ def test_pipelined_host_batches_equal_single_piece_batches():
         assert np.array_equal(raw, p.project(*poses, max_ray_length=carm.max_ray_length))
 
 
+def test_lane_layout_does_not_change_the_images():
+    """DRR_TUNE_LANE_QUADS only changes which lane of a warp walks which pixel of its 8 x 8 tile (2 x 2 groups for the texture unit, or
+    4 x 1 runs): every pixel's ray, its samples and their order stay the same, so the images must be identical -- on odd detector
+    sizes (partial tiles) as well, and under all three samplers."""
+    vol_ = phantoms.thorax_volume((64, 64, 50), (6.4, 6.4, 8.0), seed=7)
+    for (w, h) in ((96, 80), (101, 67)):
+        carm = phantoms.MobileCArmGeometry(sensor_width=w, sensor_height=h, pixel_size=3.1 * 96 / w)
+        poses = phantoms.c2_poses(3, seed=5, carm=carm)
+        for sampler in ("hybrid", "tex", "alu"):
+            with Projector(vol_, spectrum="120KV_AL43", neglog=False, camera_intrinsics=carm.camera_intrinsics, sampler=sampler) as p:
+                out = []
+                for mode in (0, 1, 2):
+                    p.set_lane_quads(mode)
+                    out.append(p.project_line_integrals(*poses, max_ray_length=carm.max_ray_length).copy())
+                assert out[0].any()
+                assert np.array_equal(out[0], out[1]) and np.array_equal(out[1], out[2]), (w, h, sampler)
+
+
 def test_fma_pipe_sampler_on_boxes_that_start_in_the_clamped_layers():
     """Regression: scenes 110, 170, 815 and 1115 of `tools/fuzz_single.py 1500 11`.  The general-segment path of the FMA-pipe sampler
     took a sample's fraction as (x - box origin) - floor(...), which is not exact when the staged box starts in the clamped cell
