@@ -17,7 +17,9 @@
 //     energy x weight into the pixel the photon hits (detector plane = image plane of the camera).
 // Tallies are 64-bit fixed point (2^-16 eV), so the sum is exact and independent of the order in which
 // threads, launches or GPUs add their photons: any split of the photon range gives bit-identical tallies.
-#include <curand_kernel.h>
+// Organisation: a warp keeps a pool of photon records in shared memory and works on the records that wait for the same thing
+// (tracking steps, a Rayleigh sample, a Compton try) side by side -- see scatter_kernel.  The random numbers are cuRAND's
+// Philox4x32-10 stream per photon id, restated below.
 #include <math_constants.h>
 
 #include "drr_device.cuh"
