@@ -20,7 +20,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 MESH_QUERY_HITS, MESH_QUERY_TRAVEL, MESH_QUERY_SEG = 0, 1, 2
 SAMPLER_ALU, SAMPLER_TEX, SAMPLER_HYBRID = 0, 1, 2
 POST_NEGLOG, POST_NOISE, POST_CLIP, POST_COLLECTED = 1, 2, 4, 8
-TUNE_TEX_EIGHTHS, TUNE_KERNEL_VARIANT, TUNE_PIPELINE, TUNE_LANE_QUADS = 0, 1, 2, 3
+TUNE_TEX_EIGHTHS, TUNE_KERNEL_VARIANT, TUNE_PIPELINE, TUNE_LANE_QUADS, TUNE_RAYS_PER_LANE = 0, 1, 2, 3, 4
 MAX_VOLUMES, MAX_MATERIALS = 8, 16
 
 # every symbol include/drr_b200.h declares (tests check the .so exports exactly these)

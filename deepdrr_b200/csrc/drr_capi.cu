@@ -205,6 +205,7 @@ struct drr_ctx {
     int tex_eighths = 4;
     int variant = 0;  // 0: warp-cooperative march (default), 1: per-ray register-cell march
     int lane_quads = 2;  // DRR_TUNE_LANE_QUADS: 0 / 1, 2 = the library's choice (1)
+    int rays_per_lane = 0;  // DRR_TUNE_RAYS_PER_LANE: 1 / 2, 0 = by ray spacing
     // mesh buffers (device pointers, possibly owned)
     int mesh_layers = 0, max_hits = 0, n_mesh_mats = 0;
     const float* hit_alphas = nullptr;
@@ -536,6 +537,7 @@ int drr_set_tuning(drr_ctx* c, int key, int value) {  // tuning knobs (results d
     if (key == DRR_TUNE_KERNEL_VARIANT && (value == 0 || value == 1)) { c->variant = value; return DRR_OK; }
     if (key == DRR_TUNE_PIPELINE && value >= 0 && value <= 64) { c->pipeline = value; return DRR_OK; }
     if (key == DRR_TUNE_LANE_QUADS && value >= 0 && value <= 2) { c->lane_quads = value; return DRR_OK; }
+    if (key == DRR_TUNE_RAYS_PER_LANE && value >= 0 && value <= 2) { c->rays_per_lane = value; return DRR_OK; }
     return fail(c, DRR_E_INVALID, "drr_set_tuning: bad key/value %d/%d", key, value);
 }
 
@@ -838,6 +840,8 @@ int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n
 // The warp-cooperative kernel stages the voxel cells an 8x4-pixel tile touches; it pays when neighbouring
 // rays are closer than a few voxels.  Estimate the tile's footprint at the volume centre for view 0 and
 // fall back to the per-ray kernel for coarse detectors / strongly magnified set-ups.
+#define RAYS2_MAX_SPREAD 2.2f  // voxels across an 8 x 4 pixel tile up to which the single-volume march walks two rays per lane
+
 static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
     const VolHost& v = c->vols[0];
     auto dir = [&](float u, float vv, float* d) {
@@ -1023,6 +1027,8 @@ int drr_project(drr_ctx* c, int n_views, int W, int H, const float* w2i, const f
     }
     const bool lockstep_ok = V > 0 && march_slack(c, n_views, src_ijk, ijk_from_world, max_ray_length, P);
     P.lane_quads = c->lane_quads == 2 ? 1 : c->lane_quads;  // 2 x 2 lane groups (see drr_march_warp.cu: lane_u); single-volume kernel only
+    // two rays per lane while an 8 x 4 pixel tile spans at most ~2 voxels (C2 at 1536^2: 1.0; crossover between 768^2 and 640^2)
+    P.rays_per_lane = c->rays_per_lane ? c->rays_per_lane : ((single && tile_spread(c, w2i, src_ijk, ijk_from_world, W, H) <= RAYS2_MAX_SPREAD) ? 2 : 1);
     // ---- host-bound single-volume batches: two halves, the device-to-host copy of the first under the march of the second -----
     // (projector.py:786-792 copies every view back before the next one starts; here only the second half's copy is exposed)
     const bool lockstep_single = single && h_has_cells(c) && (c->variant == 0 ? lockstep_ok : true) &&

@@ -43,6 +43,7 @@ struct MarchParams {
     int tex_eighths;  // hybrid sampler: how many of every 8 consecutive steps of a fast segment use the texture unit
     float slack_lo, slack_hi, slack_alpha;  // lock-step kernels: slack of the staged box (voxels) and of the window tests (mm)
     int lane_quads;                         // march_warp_kernel: lanes 4i .. 4i+3 walk a 2 x 2 block of pixels (else a 4 x 1 run)
+    int rays_per_lane;                      // march_warp_kernel: 1 or 2 (host only: picks the instantiation)
     // meshes (K.cu:172-177); null when unused
     int mesh_layers, max_hits, n_mesh_mats;
     const float* hit_alphas;

@@ -56,7 +56,7 @@
 #define FAST_ROTATE 1                  // fast segments rotate only the ray state they use
 #endif
 #ifndef RAYS_PER_LANE
-#define RAYS_PER_LANE 2                // single-volume kernel: a warp walks an 8 x (4 * RAYS_PER_LANE) pixel tile
+#define RAYS_PER_LANE 2                // single-volume kernel: a warp walks an 8 x (4 * R) pixel tile, R = 1 or RAYS_PER_LANE per launch
 #endif
 // Slack of the staged box (MarchParams::slack_lo / slack_hi, voxels) and of the window tests (slack_alpha, mm): they cover the
 // drift of the accumulated fp32 alpha against alpha + S * step (<= S / 2 ulps of alpha; times |d| in voxels) and, on the high
@@ -700,14 +700,17 @@ __device__ __forceinline__ void march_tile(const MarchParams& P, const ViewDev& 
     march_core<NM, KTEX, false, R>(vol, P.step, sx, sy, sz, dx, dy, dz, lo, hi, alpha, num_steps, s_coef, s_code, lane, acc, P.slack_lo, P.slack_hi, P.slack_alpha);
 }
 
-template <int NM>
+// R rays per lane.  Two pay when neighbouring rays are close (C2: 0.12 voxel apart, the staged box hardly grows and its cost is
+// shared by twice the rays); with rays a third of a voxel apart and more the 8 x 8 tile's boxes outgrow the staging buffer, the
+// segments shrink, and one ray per lane is faster -- 2.2 against 3.2 ms for a 512^2 view of the C2 volume, 1.8 against 4.8 ms at
+// 384^2 (gpurun_out/r2_rays_per_lane.log).  The host picks per batch (drr_capi.cu: MarchParams::rays_per_lane).
+template <int NM, int R>
 __global__ void __launch_bounds__(32 * SWB, SMB) march_warp_kernel(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* s_coef = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WARP_SMEM);
     uint8_t* s_code_alu = smem_raw + (size_t)warp * WARP_SMEM + MAXC * 32;
     uint8_t* s_code_tex = smem_raw + (size_t)warp * WARP_SMEM;
-    constexpr int R = RAYS_PER_LANE;
     const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H * R - 1) / (TILE_H * R);
     const unsigned tiles_per_view = (unsigned)tiles_x * tiles_y;
     const unsigned n_tiles = tiles_per_view * (unsigned)P.n_views;
@@ -753,6 +756,7 @@ __global__ void __launch_bounds__(32 * SWB, SMB) march_warp_kernel(const __grid_
     if (lane == 0 && my_steps) { atomicAdd(P.sample_count, my_steps); atomicAdd(P.sample_count + 1, my_window); }
 }
 
+#ifndef MARCH_WARP_R1_UNIT
 // ---------------------------------------------------------------------------------------------
 // Multi-volume scenes (BASELINE C3: a CT plus tool volumes).  Along most of every ray only one volume can be picked,
 // and there the march is the single-volume one above -- provided the reference's shared label cache (K.cu:394-396,
@@ -952,29 +956,47 @@ cudaError_t drr_launch_march_multi(const MarchParams& P, int n_sm, cudaStream_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NM>
-static cudaError_t launch_warp_nm(const MarchParams& P, int n_sm, cudaStream_t s) {
+#endif  // !MARCH_WARP_R1_UNIT
+template <int NM, int R>
+static cudaError_t launch_warp_nm_r(const MarchParams& P, int n_sm, cudaStream_t s) {
     const size_t smem = (size_t)WARP_SMEM * SWB;
-    cudaError_t e = cudaFuncSetAttribute(march_warp_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(march_warp_kernel<NM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_warp_kernel<NM>, 32 * SWB, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, march_warp_kernel<NM, R>, 32 * SWB, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    march_warp_kernel<NM><<<n_sm * occ, 32 * SWB, smem, s>>>(P);
+    march_warp_kernel<NM, R><<<n_sm * occ, 32 * SWB, smem, s>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t drr_launch_march_warp(const MarchParams& P, int n_sm, cudaStream_t s) {
+// The one-ray-per-lane instantiations are compiled in their own translation unit (drr_march_warp_r1.cu includes this file with
+// MARCH_WARP_R1_UNIT defined), so that the two halves build in parallel.
+#ifdef MARCH_WARP_R1_UNIT
+#define MARCH_WARP_R 1
+#define MARCH_WARP_LAUNCH drr_launch_march_warp_r1
+#else
+#define MARCH_WARP_R RAYS_PER_LANE
+#define MARCH_WARP_LAUNCH launch_march_warp_r2
+cudaError_t drr_launch_march_warp_r1(const MarchParams& P, int n_sm, cudaStream_t s);
+static
+#endif
+cudaError_t MARCH_WARP_LAUNCH(const MarchParams& P, int n_sm, cudaStream_t s) {
     switch (P.M) {
-        case 1: return launch_warp_nm<1>(P, n_sm, s);
-        case 2: return launch_warp_nm<2>(P, n_sm, s);
-        case 3: return launch_warp_nm<3>(P, n_sm, s);
-        case 4: return launch_warp_nm<4>(P, n_sm, s);
-        case 5: return launch_warp_nm<5>(P, n_sm, s);
-        case 6: return launch_warp_nm<6>(P, n_sm, s);
-        case 7: return launch_warp_nm<7>(P, n_sm, s);
-        case 8: return launch_warp_nm<8>(P, n_sm, s);
+        case 1: return launch_warp_nm_r<1, MARCH_WARP_R>(P, n_sm, s);
+        case 2: return launch_warp_nm_r<2, MARCH_WARP_R>(P, n_sm, s);
+        case 3: return launch_warp_nm_r<3, MARCH_WARP_R>(P, n_sm, s);
+        case 4: return launch_warp_nm_r<4, MARCH_WARP_R>(P, n_sm, s);
+        case 5: return launch_warp_nm_r<5, MARCH_WARP_R>(P, n_sm, s);
+        case 6: return launch_warp_nm_r<6, MARCH_WARP_R>(P, n_sm, s);
+        case 7: return launch_warp_nm_r<7, MARCH_WARP_R>(P, n_sm, s);
+        case 8: return launch_warp_nm_r<8, MARCH_WARP_R>(P, n_sm, s);
         default: return cudaErrorInvalidValue;
     }
 }
+
+#ifndef MARCH_WARP_R1_UNIT
+cudaError_t drr_launch_march_warp(const MarchParams& P, int n_sm, cudaStream_t s) {
+    return P.rays_per_lane == 1 ? drr_launch_march_warp_r1(P, n_sm, s) : launch_march_warp_r2(P, n_sm, s);
+}
+#endif  // !MARCH_WARP_R1_UNIT

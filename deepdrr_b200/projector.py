@@ -636,5 +636,11 @@ class Projector(object):
         Results do not depend on it."""
         _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_LANE_QUADS, int(mode)), self._h)
 
+    def set_rays_per_lane(self, rays: int):
+        """Rays a lane of the single-volume lock-step march walks through each staged box: 1, 2, or 0 = by ray spacing (default).
+        The samples and their order do not depend on it; which of them the hybrid sampler hands to the texture unit does, so results
+        can move in the last bit (the two samplers agree to 1 ulp per fetch)."""
+        _lib.check(_lib.load().drr_set_tuning(self._h, _lib.TUNE_RAYS_PER_LANE, int(rays)), self._h)
+
     def project_over_carm_range(self, *a, **k):
         raise DeprecationError("project_over_carm_range is deprecated. See README for alternatives.")

@@ -101,11 +101,14 @@ int drr_set_march(drr_ctx* ctx, float step, int attenuate_outside_volume, int ai
  *                           last k views (at most half) apart, so that the device-to-host copy of the first piece runs
  *                           under the march of the second; 0: one piece.
  *   DRR_TUNE_LANE_QUADS     single-volume lock-step march: 1 = the four lanes the texture unit filters together walk a 2 x 2
- *                           block of pixels, 0 = a 4 x 1 run, 2 (default) = the library's choice (currently 1). */
+ *                           block of pixels, 0 = a 4 x 1 run, 2 (default) = the library's choice (currently 1).
+ *   DRR_TUNE_RAYS_PER_LANE  single-volume lock-step march: rays a lane walks through each staged box, 1 or 2; 0 (default) = chosen
+ *                           per batch from the ray spacing (two while an 8 x 4 pixel tile spans at most ~2 voxels). */
 #define DRR_TUNE_TEX_EIGHTHS 0
 #define DRR_TUNE_KERNEL_VARIANT 1
 #define DRR_TUNE_PIPELINE 2
 #define DRR_TUNE_LANE_QUADS 3
+#define DRR_TUNE_RAYS_PER_LANE 4
 int drr_set_tuning(drr_ctx* ctx, int key, int value);
 
 /* Mesh inputs of projectKernel (project_kernel.cu:172-177, 363-375, 498-517, 569-579), per view,

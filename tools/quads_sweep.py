@@ -18,6 +18,13 @@ for n in [int(a) for a in sys.argv[1:]] or [1536, 1152, 1024, 768, 640, 512]:
     with Projector(v2, spectrum="120KV_AL43", step=0.1, neglog=True, camera_intrinsics=carm.camera_intrinsics,
                    source_to_detector_distance=carm.source_to_detector_distance, sampler="hybrid") as p:
         out = {}
+        for rays in (1, 2, 0):   # 0 = the library's choice from the ray spacing
+            p.set_rays_per_lane(rays)
+            best = 1e9
+            for r in range(3):
+                img = p.project(*poses, max_ray_length=carm.max_ray_length)
+                best = min(best, p.last_timing_ms()["march"])
+            print(f"  {n}^2 rays_per_lane={rays}: {best / nv:.3f} ms/view, {best / nv / (n * n) * 1e6:.3f} ms per Mray", flush=True)
         for mode in (0, 1, 0, 1):
             p.set_lane_quads(mode)
             best = 1e9
