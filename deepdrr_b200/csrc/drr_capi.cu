@@ -452,13 +452,13 @@ static int add_volume_impl(drr_ctx* c, const float* density, const uint8_t* labe
         {
             size_t free_b = 0, total_b = 0;
             const size_t want = ncell * 2 * sizeof(float4), tex_bytes = (flags & 2u) ? 0 : n * sizeof(float);
-            cudaError_t e_ = cudaMemGetInfo(&free_b, &total_b);
-            if ((flags & 4u) || (e_ == cudaSuccess && !(flags & 2u) && want + tex_bytes + (size_t)(1u << 28) > free_b)) {
+            cudaError_t info = cudaMemGetInfo(&free_b, &total_b);
+            if ((flags & 4u) || (info == cudaSuccess && !(flags & 2u) && want + tex_bytes + (size_t)(1u << 28) > free_b)) {
                 v.cellc = nullptr;
             } else {
-                e_ = cudaMalloc(&v.cellc, want);
-                if (e_ == cudaErrorMemoryAllocation && !(flags & 2u)) { cudaGetLastError(); v.cellc = nullptr; }
-                else CUV(e_);
+                const cudaError_t got = cudaMalloc(&v.cellc, want);  // (not named e_: CUV declares its own e_)
+                if (got == cudaErrorMemoryAllocation && !(flags & 2u)) { cudaGetLastError(); v.cellc = nullptr; }
+                else CUV(got);
             }
         }
         dim3 cg((ni + 1 + 127) / 128, nj + 1, nk + 1);
@@ -840,6 +840,9 @@ int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n
 // The warp-cooperative kernel stages the voxel cells an 8x4-pixel tile touches; it pays when neighbouring
 // rays are closer than a few voxels.  Estimate the tile's footprint at the volume centre for view 0 and
 // fall back to the per-ray kernel for coarse detectors / strongly magnified set-ups.
+#ifndef PER_RAY_MIN_SPREAD
+#define PER_RAY_MIN_SPREAD 4.0f  // voxels across an 8 x 4 pixel tile beyond which the per-ray kernel takes over
+#endif
 #define RAYS2_MAX_SPREAD 2.2f  // voxels across an 8 x 4 pixel tile up to which the single-volume march walks two rays per lane
 
 static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
@@ -863,7 +866,7 @@ static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, c
 
 static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
     if (c->variant != 0) return c->variant;
-    return tile_spread(c, w2i, src, ijk, W, H) > 4.0f ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
+    return tile_spread(c, w2i, src, ijk, W, H) > PER_RAY_MIN_SPREAD ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
 }
 
 // Slack of the lock-step kernels' staged boxes and window tests for this batch (see drr_march_warp.cu).  A segment of S steps is
