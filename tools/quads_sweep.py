@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Development (GPU box): the lane layout of the single-volume march (DRR_TUNE_LANE_QUADS) against the ray spacing.
+"""Development (GPU box): rays per lane (DRR_TUNE_RAYS_PER_LANE) and lane layout (DRR_TUNE_LANE_QUADS) of the single-volume march
+against the ray spacing.
 
 One resident C2 volume, the bench's first poses, the same field of view on detectors of N^2 pixels: march ms per view and
-per 10^6 rays with 2 x 2 lane groups (1) and 4 x 1 runs (0); the images must be identical.
+per 10^6 rays with one / two rays per lane and the library's own choice (0), then with 2 x 2 lane groups (1) and 4 x 1 runs (0),
+for which the images must be identical.
 """
 import os, sys
 import numpy as np
