@@ -843,9 +843,10 @@ int drr_mesh_clean_hits(drr_ctx* c, float* ts, int8_t* facing, int n_rays, int n
 #ifndef PER_RAY_MIN_SPREAD
 #define PER_RAY_MIN_SPREAD 4.0f  // voxels across an 8 x 4 pixel tile beyond which the per-ray kernel takes over
 #endif
+#define PER_RAY_MIN_STEP_VOX 0.9f  // voxels per step beyond which the per-ray kernel takes over
 #define RAYS2_MAX_SPREAD 2.2f  // voxels across an 8 x 4 pixel tile up to which the single-volume march walks two rays per lane
 
-static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
+static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H, float* vox_per_mm = nullptr) {
     const VolHost& v = c->vols[0];
     auto dir = [&](float u, float vv, float* d) {
         float r[3];
@@ -861,12 +862,18 @@ static float tile_spread(const drr_ctx* c, const float* w2i, const float* src, c
     float alpha_c = dd > 0 ? (ctr[0] * d0[0] + ctr[1] * d0[1] + ctr[2] * d0[2]) / dd : 0.0f;
     float spread = 0.0f;
     for (int a = 0; a < 3; a++) spread = fmaxf(spread, fabsf(alpha_c * (d1[a] - d0[a])));
+    if (vox_per_mm) *vox_per_mm = sqrtf(dd);  // voxels per mm along the central ray
     return spread;
 }
 
 static int pick_variant(const drr_ctx* c, const float* w2i, const float* src, const float* ijk, int W, int H) {
     if (c->variant != 0) return c->variant;
-    return tile_spread(c, w2i, src, ijk, W, H) > PER_RAY_MIN_SPREAD ? 1 : 0;  // more than ~4 voxels across a tile: per-ray kernel
+    float vox_per_mm = 0.0f;
+    const float spread = tile_spread(c, w2i, src, ijk, W, H, &vox_per_mm);
+    // more than ~4 voxels across a tile, or steps of about a voxel and more (the 32 steps of a segment then cover so many cells that
+    // the staged boxes have to be cut down again and again: C2 at a step of 1 mm, 1.25 voxels, 5.5 against 4.8 ms per view; at 2 mm
+    // 5.7 against 2.5; at 0.5 mm the lock-step kernel is still 1.7 x faster -- tools/step_sweep.py): per-ray kernel
+    return (spread > PER_RAY_MIN_SPREAD || c->step * vox_per_mm > PER_RAY_MIN_STEP_VOX) ? 1 : 0;
 }
 
 // Slack of the lock-step kernels' staged boxes and window tests for this batch (see drr_march_warp.cu).  A segment of S steps is

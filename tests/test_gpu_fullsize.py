@@ -121,6 +121,33 @@ def test_fine_grid_far_source_single_volume_vs_live_reference(spacing, distance)
     refl.close()
 
 
+@pytest.mark.parametrize("step", [0.3, 1.0, 2.5, 7.0])
+def test_long_steps_vs_live_reference(step):
+    """Steps from a third of a voxel to several voxels (1 mm voxels).  The lock-step kernels stage the cells of up to 32 steps at a
+    time and have to cut their segments down when the steps are long; from about a voxel per step the host hands the scene to the
+    per-ray kernel (drr_capi.cu: pick_variant).  Either way the samples are the reference's."""
+    ref_gpu = _ref()
+    vol = phantoms.thorax_volume((160, 128, 120), (1.0, 1.0, 1.0), seed=3)
+    st = cases.tables([vol], "90KV_AL40", None)
+    W, H = 320, 256
+    k = geo.CameraIntrinsicTransform.from_sizes((W, H), 0.6, 1000.0)   # rays 0.3 voxel apart at the volume
+    refl = ref_gpu.RefProjector([vol.data], st.labels, st.M, lineint=True)
+    poses = [phantoms.look_at_projection(-500.0 * np.asarray(d) / np.linalg.norm(d), np.asarray(d) / np.linalg.norm(d), (0, 0, 1), k)
+             for d in ((0.3, 1.0, 0.2), (1.0, 0.1, -0.4))]
+    for i, pose in enumerate(poses):
+        w2i, src, ijk = geo.pose_arrays(pose, [vol])
+        li = refl.line_integrals(W, H, step, w2i, src, ijk, 1200.0)
+        assert (li > 0).any()
+        for sampler in ("hybrid", "tex", "alu"):
+            with Projector(vol, spectrum="90KV_AL40", step=step, neglog=False, camera_intrinsics=k, source_to_detector_distance=1000.0,
+                           sampler=sampler) as p:
+                for variant in (0, 1):   # 0: the library's choice, 1: the per-ray kernel
+                    p.set_kernel_variant(variant)
+                    area = p.project_line_integrals(pose, max_ray_length=1200.0)
+                    _check(area[0], None, li, None, f"step {step} mm pose {i} [{sampler}, variant {variant}]")
+    refl.close()
+
+
 def test_five_volumes_vs_live_reference():
     """More volumes than the lock-step kernels are built for (4): the step-by-step kernel's wide instantiation
     (csrc/drr_march.cu, DRR_MAX_VOLUMES x DRR_MAX_MATERIALS register arrays, counts read at run time) against the reference
